@@ -1,0 +1,158 @@
+/*
+ * vila_b200 — C-ABI of the B200-native (sm_100a) VILA multimodal forward hot path.
+ *
+ * The reference (NVlabs/VILA) has no FFI on this path: every GPU op is a library call made from
+ * Python (flash_attn, cuBLAS through nn.Linear, cuDNN through nn.Conv2d, ATen elementwise).  This
+ * header is the boundary a maintainer would bind instead of those calls; each entry point names the
+ * reference call site (paths relative to the VILA repo root) it replaces.  The only native-extension
+ * precedent in the tree (llava/model/coat/optimizer/kernels/bindings.cpp:6-10) takes tensors,
+ * mutates in place, returns void and runs on the current stream; we keep "caller owns all memory,
+ * in-place/out-param, stream-ordered", but with plain pointers so any host language can bind it.
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers to bf16 (uint16 storage) unless stated otherwise,
+ *     row-major, 16-byte aligned; leading dimensions are in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns 0 on success; non-zero on error, message via vila_last_error()
+ *     (thread-local). Nothing falls back to the CPU: without an sm_100a device calls fail.
+ *   - no hidden global state: KV pool, page tables, workspaces and counters are caller-allocated.
+ */
+#ifndef VILA_B200_H_
+#define VILA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VILA_ACT_NONE 0
+#define VILA_ACT_GELU_TANH 1 /* SigLIP "gelu_pytorch_tanh"  (modeling_siglip.py:707-715) */
+#define VILA_ACT_GELU_ERF 2  /* nn.GELU() in mm_projector   (base_projector.py:145-162)  */
+#define VILA_ACT_SILU 3
+
+const char* vila_last_error(void);
+int vila_abi_version(void);
+/* fills SM count and compute capability of the current device */
+int vila_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * vila_linear — out[M,N] = epilogue(x[M,K] · w[N,K]^T)        (tcgen05 / TMEM / TMA GEMM)
+ *   epilogue: (+bias[N]) -> act -> (+residual[row % res_row_mod or row, :])   or SwiGLU:
+ *   swiglu != 0: w rows are interleaved (gate_0, up_0, gate_1, up_1, ...) and out is [M, N/2] =
+ *   silu(gate) * up.
+ * Replaces nn.Linear (+ the ATen GELU / SiLU*mul / residual add that follows it):
+ *   SigLIP q/k/v/out_proj, fc1/fc2 : llava/model/multimodal_encoder/siglip/modeling_siglip.py:384-387,707-715,752,757
+ *   patch-embed Conv2d (as im2col GEMM, residual = position embedding with res_row_mod = #patches): :269-275,322-328
+ *   mm_projector Linear layers     : llava/model/multimodal_projector/base_projector.py:145-162
+ *   Qwen2 q/k/v/o, gate/up/down, lm_head: transformers Qwen2 (in-tree copy
+ *     llava/eval/vision_niah_vila/zigzag_ring_attn/modeling_qwen2.py:164-176,223-226,633-706)
+ * ------------------------------------------------------------------------------------------- */
+int vila_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const void* bias,
+                const void* residual, int64_t ld_res, int res_row_mod, void* out, int64_t ldo,
+                int M, int N, int K, int act, int swiglu, void* stream);
+/* test hook: same, forcing the N tile (64 / 128 / 256) */
+int vila_linear_cfg(int block_n, const void* x, int64_t ldx, const void* w, int64_t ldw,
+                    const void* bias, const void* residual, int64_t ld_res, int res_row_mod,
+                    void* out, int64_t ldo, int M, int N, int K, int act, int swiglu, void* stream);
+
+/* nn.LayerNorm over the last dim (modeling_siglip.py:723,725,746,755; base_projector.py:147) */
+int vila_layernorm(const void* x, const void* weight, const void* bias, void* out, int rows,
+                   int cols, float eps, void* stream);
+/* Qwen2RMSNorm (modeling_qwen2.py:81-95). If residual_add != NULL: x += residual_add first (in place). */
+int vila_rmsnorm(void* x_inout, const void* residual_add, const void* weight, void* out, int rows,
+                 int cols, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * vila_fmha — flash attention forward, tcgen05 QK^T / PV with TMEM accumulators.
+ *   q/o element (token t, head h, dim d) at  base + t*tok_stride + h*head_stride + d
+ *   k/v: if kv_page_stride != 0 the KV cache is paged (128 tokens per page):
+ *          element (page p, row r, head h, d) at base + p*kv_page_stride + r*kv_tok_stride + h*kv_head_stride + d
+ *          and page_table[b*page_table_stride + j] gives the page of block j (NULL: identity);
+ *        else k/v are [B*Sk, Hkv, D] views like q.
+ * Replaces flash_attn_func(q,k,v,causal=False) in SiglipFlashAttention2 (modeling_siglip.py:583-585)
+ * and HF _flash_attention_forward for Qwen2/Llama (patched at llava/train/sequence_parallel/
+ * monkey_patch.py:133-239, llava/model/utils/packing.py:36), causal GQA.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct vila_fmha_params {
+  const void* q;
+  int64_t q_tok_stride, q_head_stride;
+  const void* k;
+  const void* v;
+  int64_t kv_page_stride, kv_tok_stride, kv_head_stride, kv_num_pages;
+  const int32_t* page_table;
+  int32_t page_table_stride;
+  void* o;
+  int64_t o_tok_stride, o_head_stride;
+  int32_t B, Sq, Sk, Hq, Hkv, D, causal;
+  float scale;
+} vila_fmha_params;
+int vila_fmha(const vila_fmha_params* p, void* stream);
+
+/* im2col for Conv2d(3,1152,k=14,s=14) (modeling_siglip.py:269-275): pixels [B,C,H,W] ->
+ * out [B*(H/P)*(W/P), k_pad], column = (c, ky, kx); columns >= C*P*P are zero. */
+int vila_patch_im2col(const void* pixels, void* out, int B, int C, int H, int W, int patch,
+                      int k_pad, void* stream);
+/* DownSampleBlock.flat_square / flat_square_2x2 / flat_square_3x3 (base_projector.py:58-123):
+ * x [B, h*w, C] -> out [B, ceil(h/r)*ceil(w/r), r*r*C], zero padded. */
+int vila_space_to_depth(const void* x, void* out, int B, int h, int w, int C, int r, void* stream);
+/* merge_features_for_dynamic_s2 + split_chessboard for one image (llava_arch.py:282-364). */
+int vila_s2_merge(const void* tiles, void* out, int side, int C, int n_scales,
+                  const int* splits_h, const int* splits_w, int out_bh, int out_bw, int share_tile,
+                  void* stream);
+/* merge_chessboard + "(h w) c" flatten of projected tiles (llava_arch.py:255-280,384-390). */
+int vila_chessboard_merge(const void* tiles, void* out, int bh, int bw, int s, int C, void* stream);
+/* TSPVideoEncoder pooling (llava/model/encoders/video/tsp.py:11-12,28-51). */
+int vila_tsp_pool(const void* x, void* out, int T, int h, int w, int C, int pt, int ph, int pw,
+                  void* stream);
+/* text/media embedding splice of LlavaMetaForCausalLM._embed (llava_arch.py:429,457-479):
+ * out[i] = src[i] >= 0 ? table[src[i]] : media[-(src[i]+1)].  src is int32 on the device. */
+int vila_embed_splice(const void* table, const void* media, const int32_t* src, void* out, int rows,
+                      int cols, void* stream);
+/* HF apply_rotary_pos_emb (modeling_qwen2.py:99-160) in place on q,k of qkv [S,(Hq+2Hkv)*D] and
+ * DynamicCache.update as a scatter into the paged pool (k_pool may be NULL: RoPE only).
+ * inv_freq: fp32 [D/2] on the device. positions: int32 [S] on the device. */
+int vila_rope_kv_append(void* qkv, const int32_t* positions, int S, int Hq, int Hkv, int D,
+                        const float* inv_freq, void* k_pool, void* v_pool,
+                        const int32_t* page_table, int cache_pos0, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * decode (one token): weight-streaming GEMV with fused RMSNorm prologue and bias / residual /
+ * SwiGLU / greedy-argmax epilogues; split-KV paged GQA attention with fused RoPE + KV append.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct vila_gemv_params {
+  const void* x;
+  const void* w;
+  const void* bias;
+  const void* norm_w;
+  float norm_eps;
+  const void* residual;
+  void* y;
+  int32_t N, K, swiglu;
+  unsigned long long* argmax_key; /* device u64, zero before the first launch */
+} vila_gemv_params;
+int vila_gemv(const vila_gemv_params* p, void* stream);
+
+int vila_argmax_finalize(unsigned long long* key, int32_t* token_out, int32_t* token_hist,
+                         int32_t* step_counter, int32_t* position, const void* embed_table,
+                         void* x_next, int hidden, void* stream);
+
+typedef struct vila_decode_attn_params {
+  void* qkv;
+  const int32_t* position;
+  void* k_pool;
+  void* v_pool;
+  const int32_t* page_table;
+  void* out;
+  float* ws;         /* >= Hkv*num_splits*G*(D+2) floats */
+  int32_t* counters; /* Hkv ints, zero-initialised once */
+  const float* inv_freq;
+  int32_t Hq, Hkv, D, num_splits;
+  float scale;
+} vila_decode_attn_params;
+int vila_decode_attention(const vila_decode_attn_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VILA_B200_H_ */

@@ -1,0 +1,259 @@
+"""Pin the oracle against the reference's own code, executed in the authoring container.
+
+Runs ONLY where /root/reference exists (never on the GPU box, never from tests/ or bench.py).
+  * vendored SigLIP (modeling_siglip.py) and MultimodalProjector (base_projector.py) are loaded by
+    file path and run on random-init weights;
+  * the llava_arch.py glue (merge_chessboard / split_chessboard / merge_features_for_dynamic_s2 /
+    encode_images / _embed / __batchify_sequence) and the TSP encoder cannot be imported as a package
+    here (deepspeed / hydra / accelerate missing), so their function bodies are extracted from the
+    reference source with `ast` and executed unmodified against stub objects;
+  * the Qwen2 arithmetic (third-party transformers==4.46.0 in the reference) is checked against the
+    installed transformers Qwen2ForCausalLM (sdpa + eager).
+Prints max-abs differences; exits non-zero if any exceeds its tolerance.
+"""
+from __future__ import annotations
+
+import ast
+import importlib.util
+import sys
+import textwrap
+import types
+from collections import defaultdict, deque
+from pathlib import Path
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from oracle import vila_oracle as O  # noqa: E402
+
+REF = Path("/root/reference")
+FAILED = []
+
+
+def report(name, diff, tol):
+    ok = diff <= tol
+    print(f"[{'ok' if ok else 'FAIL'}] {name:58s} max|diff| = {diff:.3e} (tol {tol:.1e})")
+    if not ok:
+        FAILED.append(name)
+
+
+def load_by_path(name: str, path: Path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def extract_functions(path: Path, names):
+    """Return {name: source} for (possibly nested-in-class) function defs in a reference file."""
+    src = path.read_text()
+    tree = ast.parse(src)
+    out = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in out:
+            seg = ast.get_source_segment(src, node)
+            # drop decorators such as @staticmethod
+            out[node.name] = textwrap.dedent(seg)
+    return out
+
+
+# -------------------------------------------------------------------------------------------------
+def check_siglip():
+    import transformers  # noqa: F401  (import real names before stubbing)
+    siglip_dir = REF / "llava/model/multimodal_encoder/siglip"
+    ms = load_by_path("ref_modeling_siglip", siglip_dir / "modeling_siglip.py")
+    import transformers.models.siglip.configuration_siglip as cfgmod
+    torch.manual_seed(0)
+    for attn in ("eager", "sdpa"):
+        cfg = cfgmod.SiglipVisionConfig(hidden_size=144, intermediate_size=272, num_hidden_layers=4,
+                                        num_attention_heads=2, image_size=56, patch_size=14)
+        cfg._attn_implementation = attn
+        model = ms.SiglipVisionModel(cfg).eval()
+        # give biases / LN params non-trivial values
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if p.dim() == 1:
+                    p.normal_(0, 0.1)
+                    if "layer_norm" in n and n.endswith("weight"):
+                        p.add_(1.0)
+        px = torch.randn(2, 3, 56, 56)
+        with torch.no_grad():
+            ref = model(px, output_hidden_states=True).hidden_states[-2]
+        sd = {k: v for k, v in model.state_dict().items()}
+        ocfg = O.SiglipCfg(hidden_size=144, intermediate_size=272, num_hidden_layers=4,
+                           num_attention_heads=2, image_size=56, patch_size=14)
+        mine = O.siglip_tower(px, sd, ocfg, -2)
+        report(f"siglip_tower hidden_states[-2] vs reference ({attn})", (ref - mine).abs().max().item(), 2e-5)
+    return ms
+
+
+def check_projector():
+    import transformers  # noqa: F401
+    # base_projector imports timm.models.layers.Mlp only for the PS3 head -> 3-line stub
+    timm = types.ModuleType("timm"); timm_m = types.ModuleType("timm.models")
+    timm_l = types.ModuleType("timm.models.layers")
+    timm_l.Mlp = type("Mlp", (torch.nn.Module,), {})
+    sys.modules.setdefault("timm", timm); sys.modules.setdefault("timm.models", timm_m)
+    sys.modules.setdefault("timm.models.layers", timm_l)
+    bp = load_by_path("refprojector", REF / "llava/model/multimodal_projector/base_projector.py")
+    torch.manual_seed(1)
+    for kind, n_tok in (("mlp_downsample", 64), ("mlp_downsample", 49), ("mlp_downsample_2x2_fix", 49),
+                        ("mlp_downsample_3x3_fix", 64), ("mlp_downsample_3x3_fix", 81)):
+        cfg = types.SimpleNamespace(mm_hidden_size=48, hidden_size=96)
+        pc = bp.MultimodalProjectorConfig(kind)
+        model = bp.MultimodalProjector(pc, cfg).eval()
+        with torch.no_grad():
+            for p in model.parameters():
+                if p.dim() == 1:
+                    p.normal_(0, 0.2)
+        x = torch.randn(3, n_tok, 48)
+        with torch.no_grad():
+            ref = model(x)
+        mine = O.projector(x, dict(model.state_dict()), kind)
+        report(f"projector {kind} N={n_tok}", (ref - mine).abs().max().item(), 1e-5)
+    # flat_square on non-square grids (w != h) directly
+    x = torch.randn(2, 5, 7, 8)
+    report("flat_square_2x2 5x7", (bp.flat_square_2x2(x) - O.flat_square(x, 2)).abs().max().item(), 0)
+    report("flat_square_3x3 5x7", (bp.flat_square_3x3(x) - O.flat_square(x, 3)).abs().max().item(), 0)
+    report("DownSampleBlock.flat_square 5x7",
+           (bp.DownSampleBlock().flat_square(x) - O.flat_square(x, 2)).abs().max().item(), 0)
+
+
+def check_arch_glue():
+    from einops import rearrange
+    names = ["merge_chessboard", "split_chessboard", "merge_features_for_dynamic_s2", "encode_images",
+             "_embed", "__embed_media_tokens", "__truncate_sequence", "__batchify_sequence"]
+    srcs = extract_functions(REF / "llava/model/llava_arch.py", names)
+    ns = {"torch": torch, "F": F, "rearrange": rearrange, "Optional": object, "Tuple": object,
+          "Dict": dict, "List": list, "Any": object, "deque": deque, "defaultdict": defaultdict,
+          "IGNORE_INDEX": -100, "get_pg_manager": lambda: None, "warnings": __import__("warnings"),
+          "chain": __import__("itertools").chain, "distributed": None}
+    body = "class RefArch:\n"
+    for n in names:
+        s = srcs[n].replace("@staticmethod\n", "")
+        body += textwrap.indent(("@staticmethod\n" if n in ("merge_chessboard", "split_chessboard") else "") + s, "    ") + "\n"
+    exec(compile(body, "<reference llava_arch excerpts>", "exec"), ns)
+    RefArch = ns["RefArch"]
+
+    torch.manual_seed(2)
+    x = torch.randn(6, 16, 8)
+    report("merge_chessboard 2x3", (RefArch.merge_chessboard(x, 2, 3) - O.merge_chessboard(x, 2, 3)).abs().max().item(), 0)
+    y = torch.randn(1, 8, 8, 12)
+    report("split_chessboard 2x3", (RefArch.split_chessboard(y, 2, 3) - O.split_chessboard(y, 2, 3)).abs().max().item(), 0)
+
+    # dynamic-S2 encode_images with a fake tower / projector
+    C_, side = 8, 4
+    lin = torch.nn.Linear(3 * 4 * C_, 16)
+
+    class Tower:
+        scales = [4, 8, 12]
+        resize_output_to_scale_idx = -1
+
+        def __call__(self, images):
+            return images  # tests feed features directly
+
+    for idx in (-1, 0, 1):
+        tower = Tower(); tower.resize_output_to_scale_idx = idx
+        proj = lambda f: lin(O.downsample(f, 2))
+        self_ = RefArch()
+        self_.config = types.SimpleNamespace(dynamic_s2=True)
+        self_.get_vision_tower = lambda: tower
+        self_.get_mm_projector = lambda: proj
+        block_sizes = [(2, 3), None, (1, 2)]
+        n_tiles = (1 + 4 + 6) + 1 + (1 + 4 + 2)
+        feats = torch.randn(n_tiles, side * side, C_)
+        with torch.no_grad():
+            ref = self_.encode_images(feats, block_sizes)
+            mine = O.encode_images(feats, tower, proj, dynamic_s2=True, block_sizes=block_sizes,
+                                   scales=tower.scales, resize_output_to_scale_idx=idx)
+        assert type(ref) is type(mine) and len(ref) == len(mine)
+        d = max((a - b).abs().max().item() for a, b in zip(ref, mine))
+        report(f"encode_images dynamic_s2 resize_idx={idx}", d, 1e-6)
+
+    # _embed splice
+    V, H = 50, 8
+    table = torch.randn(V, H)
+    self_ = RefArch()
+    self_.training = False
+    self_.llm = types.SimpleNamespace(model=types.SimpleNamespace(embed_tokens=lambda ids: F.embedding(ids, table)))
+    IMG, VID = 40, 41
+    self_.tokenizer = types.SimpleNamespace(media_token_ids={"image": IMG, "video": VID},
+                                            padding_side="right", model_max_length=4096)
+    m_img = [torch.randn(5, H), torch.randn(3, H)]
+    m_vid = [torch.randn(7, H)]
+    self_.encoders = {"image": lambda media, cfg: list(media), "video": lambda media, cfg: list(media)}
+    for side_ in ("right", "left"):
+        self_.tokenizer.padding_side = side_
+        ids = torch.tensor([[1, 2, IMG, 3, VID, 4, 0, 0], [IMG, 9, 8, 7, 6, 5, 4, 3]])
+        am = torch.tensor([[1, 1, 1, 1, 1, 1, 0, 0], [1, 1, 1, 1, 1, 1, 1, 1]], dtype=torch.bool)
+        ref_in, ref_lab, ref_mask = getattr(self_, "_embed")(ids, {"image": list(m_img), "video": list(m_vid)},
+                                                            {"image": {}, "video": {}}, None, am)
+        my_in, my_lab, my_mask = O.embed_splice(ids, table, {"image": list(m_img), "video": list(m_vid)},
+                                                {"image": IMG, "video": VID}, None, am, side_)
+        report(f"_embed splice inputs ({side_})", (ref_in - my_in).abs().max().item(), 0)
+        report(f"_embed splice labels/mask ({side_})",
+               float((ref_lab != my_lab).sum() + (ref_mask != my_mask).sum()), 0)
+
+    # TSP encoder
+    tsp_src = extract_functions(REF / "llava/model/encoders/video/tsp.py", ["pool"])
+    ns2 = {"torch": torch}
+    exec(tsp_src["pool"], ns2)
+    z = torch.randn(8, 4, 4, 6)
+    r = z
+    for dim, pp in enumerate((4, 2, 2)):
+        r = ns2["pool"](r, pp, dim)
+    m = z
+    for dim, pp in enumerate((4, 2, 2)):
+        m = O.tsp_pool(m, pp, dim)
+    report("TSP pool (4,2,2)", (r - m).abs().max().item(), 0)
+
+
+def check_qwen2():
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    torch.manual_seed(3)
+    for attn in ("eager", "sdpa"):
+        hcfg = Qwen2Config(hidden_size=128, intermediate_size=320, num_hidden_layers=3,
+                           num_attention_heads=4, num_key_value_heads=2, vocab_size=512,
+                           rms_norm_eps=1e-6, rope_theta=1000000.0, max_position_embeddings=4096,
+                           tie_word_embeddings=False, attn_implementation=attn)
+        model = Qwen2ForCausalLM(hcfg).eval()
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if "norm" in n:
+                    p.normal_(1.0, 0.1)
+                elif p.dim() == 1:
+                    p.normal_(0, 0.1)
+        sd = dict(model.state_dict())
+        ocfg = O.Qwen2Cfg(hidden_size=128, intermediate_size=320, num_hidden_layers=3,
+                          num_attention_heads=4, num_key_value_heads=2, vocab_size=512, head_dim=32)
+        emb = torch.randn(1, 37, 128)
+        with torch.no_grad():
+            ref = model(inputs_embeds=emb).logits[0]
+            mine, _ = O.qwen2_forward(emb[0], sd, ocfg)
+        report(f"qwen2 forward logits ({attn})", (ref - mine).abs().max().item(), 5e-5)
+        with torch.no_grad():
+            gen = model.generate(inputs_embeds=emb, attention_mask=torch.ones(1, 37, dtype=torch.long),
+                                 max_new_tokens=12, do_sample=False, eos_token_id=None, pad_token_id=0)
+            ids, _ = O.greedy_generate(emb[0], sd, ocfg, 12)
+        report(f"qwen2 greedy ids ({attn})", float(sum(int(a) != int(b) for a, b in zip(gen[0].tolist(), ids))), 0)
+        # large positions (RoPE precision)
+        pos = torch.arange(60000, 60037)
+        with torch.no_grad():
+            ref = model(inputs_embeds=emb, position_ids=pos[None]).logits[0]
+            mine, _ = O.qwen2_forward(emb[0], sd, ocfg, position_ids=pos)
+        report(f"qwen2 forward logits, positions 60000+ ({attn})", (ref - mine).abs().max().item(), 5e-5)
+
+
+if __name__ == "__main__":
+    if not REF.exists():
+        print("reference tree not present: nothing to validate against")
+        sys.exit(0)
+    torch.set_num_threads(8)
+    check_siglip()
+    check_projector()
+    check_arch_glue()
+    check_qwen2()
+    print("FAILED:" if FAILED else "ALL OK", FAILED)
+    sys.exit(1 if FAILED else 0)

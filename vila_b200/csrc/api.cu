@@ -1,0 +1,202 @@
+// extern "C" surface declared in include/vila_b200.h: thin argument marshalling onto vb::*.
+#include "../../include/vila_b200.h"
+
+#include "common.cuh"
+#include "kernels.h"
+
+using bf = __nv_bfloat16;
+static inline const bf* cb(const void* p) { return static_cast<const bf*>(p); }
+static inline bf* mb(void* p) { return static_cast<bf*>(p); }
+static inline cudaStream_t st(void* s) { return static_cast<cudaStream_t>(s); }
+
+static int require_sm100() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
+      vb::set_last_error("vila_b200: no CUDA device available (this library has no CPU fallback)");
+      cudaGetLastError();
+      return 1;
+    }
+    ok = (major == 10) ? 1 : 0;
+    if (!ok) {
+      vb::set_last_error("vila_b200: built for sm_100a only, device is sm_%d%d", major, minor);
+    }
+  }
+  if (ok != 1) {
+    if (ok == 0) vb::set_last_error("vila_b200: built for sm_100a only (no fallback path)");
+    return 1;
+  }
+  return 0;
+}
+#define VB_REQUIRE_DEVICE() \
+  do {                      \
+    if (require_sm100()) return 3; \
+  } while (0)
+
+extern "C" {
+
+const char* vila_last_error(void) { return vb::last_error(); }
+int vila_abi_version(void) { return 1; }
+
+int vila_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  VB_CUDA(cudaGetDevice(&dev));
+  VB_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  VB_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  VB_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return 0;
+}
+
+static vb::GemmEpilogue make_epi(const void* bias, const void* residual, int64_t ld_res,
+                                 int res_row_mod, int act, int swiglu) {
+  vb::GemmEpilogue e;
+  e.bias = cb(bias);
+  e.residual = cb(residual);
+  e.ld_res = static_cast<int>(ld_res);
+  e.res_row_mod = res_row_mod;
+  e.act = act;
+  e.swiglu = swiglu;
+  return e;
+}
+
+int vila_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const void* bias,
+                const void* residual, int64_t ld_res, int res_row_mod, void* out, int64_t ldo,
+                int M, int N, int K, int act, int swiglu, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::gemm_bf16(cb(x), (int)ldx, cb(w), (int)ldw, mb(out), (int)ldo, M, N, K,
+                       make_epi(bias, residual, ld_res, res_row_mod, act, swiglu), st(stream));
+}
+
+int vila_linear_cfg(int block_n, const void* x, int64_t ldx, const void* w, int64_t ldw,
+                    const void* bias, const void* residual, int64_t ld_res, int res_row_mod,
+                    void* out, int64_t ldo, int M, int N, int K, int act, int swiglu, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::gemm_bf16_cfg(block_n, cb(x), (int)ldx, cb(w), (int)ldw, mb(out), (int)ldo, M, N, K,
+                           make_epi(bias, residual, ld_res, res_row_mod, act, swiglu), st(stream));
+}
+
+int vila_layernorm(const void* x, const void* weight, const void* bias, void* out, int rows,
+                   int cols, float eps, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::layernorm_bf16(cb(x), cb(weight), cb(bias), mb(out), rows, cols, eps, st(stream));
+}
+
+int vila_rmsnorm(void* x_inout, const void* residual_add, const void* weight, void* out, int rows,
+                 int cols, float eps, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::rmsnorm_bf16(mb(x_inout), cb(residual_add), cb(weight), mb(out), rows, cols, eps,
+                          st(stream));
+}
+
+int vila_fmha(const vila_fmha_params* p, void* stream) {
+  VB_REQUIRE_DEVICE();
+  vb::FmhaParams q;
+  q.q = cb(p->q);
+  q.q_tok_stride = p->q_tok_stride;
+  q.q_head_stride = p->q_head_stride;
+  q.k = cb(p->k);
+  q.v = cb(p->v);
+  q.kv_page_stride = p->kv_page_stride;
+  q.kv_tok_stride = p->kv_tok_stride;
+  q.kv_head_stride = p->kv_head_stride;
+  q.kv_num_pages = p->kv_num_pages;
+  q.page_table = p->page_table;
+  q.page_table_stride = p->page_table_stride;
+  q.o = mb(p->o);
+  q.o_tok_stride = p->o_tok_stride;
+  q.o_head_stride = p->o_head_stride;
+  q.B = p->B; q.Sq = p->Sq; q.Sk = p->Sk; q.Hq = p->Hq; q.Hkv = p->Hkv; q.D = p->D;
+  q.causal = p->causal;
+  q.scale = p->scale;
+  return vb::fmha_prefill(q, st(stream));
+}
+
+int vila_patch_im2col(const void* pixels, void* out, int B, int C, int H, int W, int patch,
+                      int k_pad, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::im2col_patch14(cb(pixels), mb(out), B, C, H, W, patch, k_pad, st(stream));
+}
+
+int vila_space_to_depth(const void* x, void* out, int B, int h, int w, int C, int r, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::space_to_depth(cb(x), mb(out), B, h, w, C, r, st(stream));
+}
+
+int vila_s2_merge(const void* tiles, void* out, int side, int C, int n_scales, const int* splits_h,
+                  const int* splits_w, int out_bh, int out_bw, int share_tile, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::s2_merge(cb(tiles), mb(out), side, C, n_scales, splits_h, splits_w, out_bh, out_bw,
+                      share_tile, st(stream));
+}
+
+int vila_chessboard_merge(const void* tiles, void* out, int bh, int bw, int s, int C, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::chessboard_merge(cb(tiles), mb(out), bh, bw, s, C, st(stream));
+}
+
+int vila_tsp_pool(const void* x, void* out, int T, int h, int w, int C, int pt, int ph, int pw,
+                  void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::tsp_pool(cb(x), mb(out), T, h, w, C, pt, ph, pw, st(stream));
+}
+
+int vila_embed_splice(const void* table, const void* media, const int32_t* src, void* out, int rows,
+                      int cols, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::embed_splice(cb(table), cb(media), src, mb(out), rows, cols, st(stream));
+}
+
+int vila_rope_kv_append(void* qkv, const int32_t* positions, int S, int Hq, int Hkv, int D,
+                        const float* inv_freq, void* k_pool, void* v_pool,
+                        const int32_t* page_table, int cache_pos0, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::rope_kv_append(mb(qkv), positions, S, Hq, Hkv, D, inv_freq, mb(k_pool), mb(v_pool),
+                            page_table, cache_pos0, st(stream));
+}
+
+int vila_gemv(const vila_gemv_params* p, void* stream) {
+  VB_REQUIRE_DEVICE();
+  vb::GemvParams g;
+  g.x = cb(p->x);
+  g.w = cb(p->w);
+  g.bias = cb(p->bias);
+  g.norm_w = cb(p->norm_w);
+  g.norm_eps = p->norm_eps;
+  g.residual = cb(p->residual);
+  g.y = mb(p->y);
+  g.N = p->N;
+  g.K = p->K;
+  g.swiglu = p->swiglu;
+  g.argmax_key = p->argmax_key;
+  return vb::gemv_bf16(g, st(stream));
+}
+
+int vila_argmax_finalize(unsigned long long* key, int32_t* token_out, int32_t* token_hist,
+                         int32_t* step_counter, int32_t* position, const void* embed_table,
+                         void* x_next, int hidden, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::argmax_finalize(key, token_out, token_hist, step_counter, position, cb(embed_table),
+                             mb(x_next), hidden, st(stream));
+}
+
+int vila_decode_attention(const vila_decode_attn_params* p, void* stream) {
+  VB_REQUIRE_DEVICE();
+  vb::DecodeAttnParams d;
+  d.qkv = mb(p->qkv);
+  d.position = p->position;
+  d.k_pool = mb(p->k_pool);
+  d.v_pool = mb(p->v_pool);
+  d.page_table = p->page_table;
+  d.out = mb(p->out);
+  d.ws = p->ws;
+  d.counters = p->counters;
+  d.inv_freq = p->inv_freq;
+  d.Hq = p->Hq; d.Hkv = p->Hkv; d.D = p->D; d.num_splits = p->num_splits;
+  d.scale = p->scale;
+  return vb::decode_attention(d, st(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,444 @@
+// Decode-time (one new token, batch 1) kernels: everything is HBM-bound weight / KV streaming.
+//
+//  gemv_kernel       y = W x (+bias)(+residual)(SwiGLU)(argmax) with a fused RMSNorm prologue.
+//                    One CTA per SM, 16 warps; each warp streams whole (row, k-part) items with
+//                    UNROLL independent 128-bit loads in flight per lane; x lives in shared memory.
+//                    Replaces cuBLAS GEMV behind nn.Linear + ATen RMSNorm/SiLU/mul/add/argmax
+//                    (modeling_qwen2.py:81-95,164-176,223-226 ; HF lm_head + greedy argmax).
+//  decode_attn_kernel  split-KV paged attention for GQA (7 query heads share one KV head), with
+//                    RoPE of q / new k and the KV append fused in (replaces apply_rotary_pos_emb,
+//                    DynamicCache.update (torch.cat) and flash_attn decode).
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vb {
+namespace {
+
+constexpr int kGemvThreads = 512;
+constexpr int kGemvWarps = kGemvThreads / 32;
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc) {
+  acc = fmaf(bf_lo(w.x), bf_lo(x.x), acc);
+  acc = fmaf(bf_hi(w.x), bf_hi(x.x), acc);
+  acc = fmaf(bf_lo(w.y), bf_lo(x.y), acc);
+  acc = fmaf(bf_hi(w.y), bf_hi(x.y), acc);
+  acc = fmaf(bf_lo(w.z), bf_lo(x.z), acc);
+  acc = fmaf(bf_hi(w.z), bf_hi(x.z), acc);
+  acc = fmaf(bf_lo(w.w), bf_lo(x.w), acc);
+  acc = fmaf(bf_hi(w.w), bf_hi(x.w), acc);
+  return acc;
+}
+
+// order-preserving float -> uint32 map (for atomicMax on packed keys)
+__device__ __forceinline__ uint32_t float_order(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(kGemvThreads, 1)
+gemv_kernel(GemvParams p, int rows_per_block, int ksplit) {
+  extern __shared__ uint4 smem_v[];
+  uint4* xs = smem_v;                                              // K/8 vectors (bf16 x)
+  float* acc = reinterpret_cast<float*>(xs + ((p.K + 7) >> 3));    // rows_per_block floats
+  __shared__ float red[32];
+  __shared__ unsigned long long best_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * rows_per_block;
+  const int nrows = min(rows_per_block, p.N - row0);
+  if (nrows <= 0) return;
+  const int nvec = p.K >> 3;
+
+  // ---- prologue: stage x (optionally RMS-normalised) in shared memory ----
+  const uint4* xg = reinterpret_cast<const uint4*>(p.x);
+  if (p.norm_w != nullptr) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const uint4 v = ldg_v4(xg + i);
+      xs[i] = v;
+      float t;
+      t = bf_lo(v.x); s += t * t;
+      t = bf_hi(v.x); s += t * t;
+      t = bf_lo(v.y); s += t * t;
+      t = bf_hi(v.y); s += t * t;
+      t = bf_lo(v.z); s += t * t;
+      t = bf_hi(v.z); s += t * t;
+      t = bf_lo(v.w); s += t * t;
+      t = bf_hi(v.w); s += t * t;
+    }
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    float t = lane < kGemvWarps ? red[lane] : 0.f;
+    t = warp_sum(t);
+    const float rstd = rsqrtf(t / p.K + p.norm_eps);
+    const uint4* wv = reinterpret_cast<const uint4*>(p.norm_w);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const uint4 v = xs[i], g = ldg_v4(wv + i);
+      uint4 o;
+      o.x = pack_bf16(bf16_round(bf_lo(v.x) * rstd) * bf_lo(g.x), bf16_round(bf_hi(v.x) * rstd) * bf_hi(g.x));
+      o.y = pack_bf16(bf16_round(bf_lo(v.y) * rstd) * bf_lo(g.y), bf16_round(bf_hi(v.y) * rstd) * bf_hi(g.y));
+      o.z = pack_bf16(bf16_round(bf_lo(v.z) * rstd) * bf_lo(g.z), bf16_round(bf_hi(v.z) * rstd) * bf_hi(g.z));
+      o.w = pack_bf16(bf16_round(bf_lo(v.w) * rstd) * bf_lo(g.w), bf16_round(bf_hi(v.w) * rstd) * bf_hi(g.w));
+      xs[i] = o;
+    }
+  } else {
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) xs[i] = ldg_v4(xg + i);
+  }
+  for (int i = threadIdx.x; i < nrows; i += blockDim.x) acc[i] = 0.f;
+  if (threadIdx.x == 0) best_s = 0ull;
+  __syncthreads();
+
+  // ---- main loop: (row, k-part) items, one warp per item, 512 B of a row per warp-load ----
+  const int nchunks = (nvec + 31) >> 5;  // 32 vectors (256 elements) per chunk
+  const int items = nrows * ksplit;
+  for (int item = warp; item < items; item += kGemvWarps) {
+    const int r = item / ksplit, part = item - r * ksplit;
+    const int c0 = (part * nchunks) / ksplit, c1 = ((part + 1) * nchunks) / ksplit;
+    const uint4* wrow = reinterpret_cast<const uint4*>(p.w + static_cast<size_t>(row0 + r) * p.K);
+    float sum = 0.f;
+    for (int c = c0; c < c1; c += UNROLL) {
+      uint4 wv[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int vi = (c + u) * 32 + lane;
+        wv[u] = (c + u < c1 && vi < nvec) ? ldg_stream(wrow + vi) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int vi = (c + u) * 32 + lane;
+        if (c + u < c1 && vi < nvec) sum = dot8(wv[u], xs[vi], sum);
+      }
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      if (ksplit == 1) acc[r] = sum;
+      else atomicAdd(&acc[r], sum);
+    }
+  }
+  __syncthreads();
+
+  // ---- epilogue ----
+  if (p.swiglu) {
+    for (int j = threadIdx.x; j < (nrows >> 1); j += blockDim.x) {
+      float g = acc[2 * j], u = acc[2 * j + 1];
+      if (p.bias) {
+        g += __bfloat162float(p.bias[row0 + 2 * j]);
+        u += __bfloat162float(p.bias[row0 + 2 * j + 1]);
+      }
+      g = bf16_round(g);
+      u = bf16_round(u);
+      p.y[(row0 >> 1) + j] = __float2bfloat16(bf16_round(silu_f(g)) * u);
+    }
+    return;
+  }
+  unsigned long long best = 0ull;
+  for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+    float v = acc[r];
+    if (p.bias) v += __bfloat162float(p.bias[row0 + r]);
+    v = bf16_round(v);
+    if (p.residual) v = bf16_round(v + __bfloat162float(p.residual[row0 + r]));
+    if (p.y) p.y[row0 + r] = __float2bfloat16(v);
+    if (p.argmax_key) {
+      const unsigned long long key =
+          (static_cast<unsigned long long>(float_order(v)) << 32) |
+          static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(row0 + r));
+      best = key > best ? key : best;
+    }
+  }
+  if (p.argmax_key) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == 0) atomicMax(&best_s, best);
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(p.argmax_key, best_s);
+  }
+}
+
+// token = argmax; append to history; bump position / step; fetch the token's embedding as the next x.
+__global__ void argmax_finalize_kernel(unsigned long long* key, int32_t* token_out,
+                                       int32_t* token_hist, int32_t* step_counter,
+                                       int32_t* position, const uint4* __restrict__ embed_table,
+                                       uint4* __restrict__ x_next, int hidden_vec) {
+  __shared__ int32_t tok_s;
+  if (threadIdx.x == 0) {
+    const unsigned long long k = *key;
+    const int32_t tok = static_cast<int32_t>(0xffffffffu - static_cast<uint32_t>(k & 0xffffffffull));
+    *token_out = tok;
+    if (token_hist && step_counter) {
+      const int32_t st = *step_counter;
+      token_hist[st] = tok;
+      *step_counter = st + 1;
+    }
+    if (position) *position = *position + 1;
+    *key = 0ull;
+    tok_s = tok;
+  }
+  __syncthreads();
+  if (embed_table != nullptr && x_next != nullptr) {
+    const uint4* src = embed_table + static_cast<size_t>(tok_s) * hidden_vec;
+    for (int i = threadIdx.x; i < hidden_vec; i += blockDim.x) x_next[i] = src[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode attention
+// ------------------------------------------------------------------------------------------------
+constexpr int kDaThreads = 256;
+constexpr int kDaWarps = 8;
+constexpr int kMaxG = 8;  // query heads per kv head
+
+template <int D, int G>
+__global__ void __launch_bounds__(kDaThreads)
+decode_attn_kernel(DecodeAttnParams p) {
+  const float* __restrict__ inv_freq = p.inv_freq;
+  static_assert(D == 128, "decode attention is specialised for head_dim 128");
+  constexpr int VPT = 8;             // elements per lane (16 bytes)
+  constexpr int LPT = D / VPT;       // lanes per token (16)
+  const int hk = blockIdx.x, split = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPT;        // which of the 2 tokens this half-warp handles
+  const int dl = lane % LPT;         // d-slice index
+  const int pos = *p.position;       // index of the new token == number of cached tokens
+  const int n_tok = pos + 1;
+
+  __shared__ float q_s[G][D];
+  __shared__ __align__(16) __nv_bfloat16 knew_s[D];
+  __shared__ __align__(16) __nv_bfloat16 vnew_s[D];
+  extern __shared__ float da_smem[];
+  float (*red_o)[G][D] = reinterpret_cast<float (*)[G][D]>(da_smem);             // [16][G][D]
+  float (*red_m)[G] = reinterpret_cast<float (*)[G]>(da_smem + kDaWarps * 2 * G * D);  // [16][G]
+  float (*red_l)[G] = red_m + kDaWarps * 2;                                       // [16][G]
+  __shared__ int is_last_s;
+
+  // ---- RoPE on the G query heads and the new key; stage in smem ----
+  const int Ht = p.Hq + 2 * p.Hkv;
+  (void)Ht;
+  for (int idx = threadIdx.x; idx < (G + 1) * (D / 2); idx += blockDim.x) {
+    const int hh = idx / (D / 2), i = idx % (D / 2);
+    const __nv_bfloat16* src =
+        hh < G ? p.qkv + (hk * G + hh) * D : p.qkv + (p.Hq + hk) * D;
+    const float x0 = __bfloat162float(src[i]), x1 = __bfloat162float(src[i + D / 2]);
+    const float ang = (float)pos * inv_freq[i];
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    cs = bf16_round(cs);
+    sn = bf16_round(sn);
+    const float y0 = bf16_round(bf16_round(x0 * cs) + bf16_round(-x1 * sn));
+    const float y1 = bf16_round(bf16_round(x1 * cs) + bf16_round(x0 * sn));
+    if (hh < G) {
+      q_s[hh][i] = y0;
+      q_s[hh][i + D / 2] = y1;
+    } else {
+      knew_s[i] = __float2bfloat16(y0);
+      knew_s[i + D / 2] = __float2bfloat16(y1);
+    }
+  }
+  for (int i = threadIdx.x; i < D; i += blockDim.x) vnew_s[i] = p.qkv[(p.Hq + p.Hkv + hk) * D + i];
+  __syncthreads();
+  if (split == 0) {  // KV append (DynamicCache.update)
+    const int page = p.page_table[pos >> 7];
+    const size_t o = ((static_cast<size_t>(page) * 128 + (pos & 127)) * p.Hkv + hk) * D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      p.k_pool[o + i] = knew_s[i];
+      p.v_pool[o + i] = vnew_s[i];
+    }
+  }
+
+  // ---- this split's token range ----
+  const int per = (n_tok + p.num_splits - 1) / p.num_splits;
+  const int t0 = split * per, t1 = min(n_tok, t0 + per);
+
+  float qreg[G][VPT];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int e = 0; e < VPT; ++e) qreg[g][e] = q_s[g][dl * VPT + e];
+
+  float m[G], l[G], o_acc[G][VPT];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    m[g] = -INFINITY;
+    l[g] = 0.f;
+#pragma unroll
+    for (int e = 0; e < VPT; ++e) o_acc[g][e] = 0.f;
+  }
+  const float sl2 = p.scale * 1.4426950408889634f;
+
+  for (int tb = t0 + warp * 2; tb < t1; tb += kDaWarps * 2) {  // warp-uniform trip count
+    const int t = tb + sub;
+    const bool valid = t < t1;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (!valid) {
+    } else if (t == pos) {
+      kv = *reinterpret_cast<const uint4*>(knew_s + dl * VPT);
+      vv = *reinterpret_cast<const uint4*>(vnew_s + dl * VPT);
+    } else {
+      const int page = p.page_table[t >> 7];
+      const size_t o = ((static_cast<size_t>(page) * 128 + (t & 127)) * p.Hkv + hk) * D + dl * VPT;
+      kv = ldg_v4(p.k_pool + o);
+      vv = ldg_v4(p.v_pool + o);
+    }
+    const float kf[VPT] = {bf_lo(kv.x), bf_hi(kv.x), bf_lo(kv.y), bf_hi(kv.y),
+                           bf_lo(kv.z), bf_hi(kv.z), bf_lo(kv.w), bf_hi(kv.w)};
+    const float vf[VPT] = {bf_lo(vv.x), bf_hi(vv.x), bf_lo(vv.y), bf_hi(vv.y),
+                           bf_lo(vv.z), bf_hi(vv.z), bf_lo(vv.w), bf_hi(vv.w)};
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < VPT; ++e) s = fmaf(qreg[g][e], kf[e], s);
+      // reduce over the 16 lanes of this half-warp
+#pragma unroll
+      for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (valid) {
+        s *= sl2;
+        const float m_new = fmaxf(m[g], s);
+        const float alpha = exp2f(m[g] - m_new);  // m == -inf -> 0
+        const float pexp = exp2f(s - m_new);
+        l[g] = l[g] * alpha + pexp;
+        // the reference's attention kernels cast probabilities to bf16 before P.V
+        const float pb = bf16_round(pexp);
+#pragma unroll
+        for (int e = 0; e < VPT; ++e) o_acc[g][e] = o_acc[g][e] * alpha + pb * vf[e];
+        m[g] = m_new;
+      }
+    }
+  }
+
+  // ---- block combine: 16 half-warp partials per head ----
+  const int slot = warp * 2 + sub;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    if (dl == 0) {
+      red_m[slot][g] = m[g];
+      red_l[slot][g] = l[g];
+    }
+#pragma unroll
+    for (int e = 0; e < VPT; ++e) red_o[slot][g][dl * VPT + e] = o_acc[g][e];
+  }
+  __syncthreads();
+  // thread -> (g, d) pairs
+  float* ws_m = p.ws;                                             // [Hkv][splits][G]
+  float* ws_l = ws_m + p.Hkv * p.num_splits * G;                  // [Hkv][splits][G]
+  float* ws_o = ws_l + p.Hkv * p.num_splits * G;                  // [Hkv][splits][G][D]
+  for (int idx = threadIdx.x; idx < G * D; idx += blockDim.x) {
+    const int g = idx / D, d = idx % D;
+    float mm = -INFINITY;
+    for (int s = 0; s < kDaWarps * 2; ++s) mm = fmaxf(mm, red_m[s][g]);
+    float ll = 0.f, oo = 0.f;
+    for (int s = 0; s < kDaWarps * 2; ++s) {
+      const float w = (red_m[s][g] == -INFINITY) ? 0.f : exp2f(red_m[s][g] - mm);
+      ll += red_l[s][g] * w;
+      oo += red_o[s][g][d] * w;
+    }
+    const size_t base = (static_cast<size_t>(hk) * p.num_splits + split) * G + g;
+    if (d == 0) {
+      ws_m[base] = mm;
+      ws_l[base] = ll;
+    }
+    ws_o[base * D + d] = oo;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(&p.counters[hk], 1);
+    is_last_s = (prev == p.num_splits - 1);
+    if (is_last_s) p.counters[hk] = 0;  // re-arm for the next launch (CUDA-graph replay)
+  }
+  __syncthreads();
+  if (!is_last_s) return;
+  __threadfence();
+  for (int idx = threadIdx.x; idx < G * D; idx += blockDim.x) {
+    const int g = idx / D, d = idx % D;
+    float mm = -INFINITY;
+    for (int s = 0; s < p.num_splits; ++s)
+      mm = fmaxf(mm, ws_m[(static_cast<size_t>(hk) * p.num_splits + s) * G + g]);
+    float ll = 0.f, oo = 0.f;
+    for (int s = 0; s < p.num_splits; ++s) {
+      const size_t base = (static_cast<size_t>(hk) * p.num_splits + s) * G + g;
+      const float ms = ws_m[base];
+      const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
+      ll += ws_l[base] * w;
+      oo += ws_o[base * D + d] * w;
+    }
+    p.out[(hk * G + g) * D + d] = __float2bfloat16(oo / ll);
+  }
+}
+
+}  // namespace
+
+int gemv_bf16(const GemvParams& p, cudaStream_t stream) {
+  VB_CHECK(p.N > 0 && p.K > 0 && p.K % 8 == 0, "gemv: bad shape N=%d K=%d (K %% 8 == 0)", p.N, p.K);
+  VB_CHECK(!p.swiglu || p.N % 2 == 0, "gemv: swiglu needs even N");
+  const int sms = num_sms();
+  int rows_per_block = (p.N + sms - 1) / sms;
+  if (p.swiglu && (rows_per_block & 1)) rows_per_block += 1;
+  const int grid = (p.N + rows_per_block - 1) / rows_per_block;
+  const int nchunks = ((p.K >> 3) + 31) >> 5;
+  int ksplit = 1;
+  while (rows_per_block * ksplit < 3 * kGemvWarps && ksplit * 2 <= nchunks && ksplit < 16) ksplit *= 2;
+  const size_t smem = static_cast<size_t>((p.K + 7) / 8) * 16 + static_cast<size_t>(rows_per_block) * 4;
+  VB_CHECK(smem <= 200 * 1024, "gemv: K=%d / rows_per_block=%d exceed shared memory", p.K,
+           rows_per_block);
+  auto kern = gemv_kernel<8>;
+  static bool attr = false;
+  if (!attr) {
+    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  kern<<<grid, kGemvThreads, smem, stream>>>(p, rows_per_block, ksplit);
+  VB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int argmax_finalize(unsigned long long* key, int32_t* token_out, int32_t* token_hist,
+                       int32_t* step_counter, int32_t* position, const __nv_bfloat16* embed_table,
+                       __nv_bfloat16* x_next, int hidden, cudaStream_t stream) {
+  VB_CHECK(hidden % 8 == 0, "argmax_finalize: hidden must be a multiple of 8");
+  argmax_finalize_kernel<<<1, 256, 0, stream>>>(key, token_out, token_hist, step_counter, position,
+                                               reinterpret_cast<const uint4*>(embed_table),
+                                               reinterpret_cast<uint4*>(x_next), hidden / 8);
+  VB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int decode_attention(const DecodeAttnParams& p, cudaStream_t stream) {
+  VB_CHECK(p.D == 128, "decode_attention: head_dim must be 128 (got %d)", p.D);
+  VB_CHECK(p.Hq % p.Hkv == 0, "decode_attention: Hq %% Hkv != 0");
+  VB_CHECK(p.num_splits >= 1 && p.num_splits <= 64, "decode_attention: bad num_splits %d",
+           p.num_splits);
+  const int G = p.Hq / p.Hkv;
+  dim3 grid(p.Hkv, p.num_splits);
+#define VB_DA_CASE(GG)                                                                          \
+  case GG: {                                                                                    \
+    auto kern = decode_attn_kernel<128, GG>;                                                    \
+    const size_t smem = (size_t)kDaWarps * 2 * GG * (128 + 2) * sizeof(float);                  \
+    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, kDaThreads, smem, stream>>>(p);                                                \
+    break;                                                                                      \
+  }
+  switch (G) {
+    VB_DA_CASE(1)
+    VB_DA_CASE(2)
+    VB_DA_CASE(4)
+    VB_DA_CASE(7)
+    VB_DA_CASE(8)
+    default:
+      set_last_error("decode_attention: unsupported GQA group size %d", G);
+      return 1;
+  }
+#undef VB_DA_CASE
+  VB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vb

@@ -1,0 +1,326 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epi(A[M,K] · W[N,K]^T)
+//
+//   * operands staged global -> shared by TMA (cp.async.bulk.tensor, 128B swizzle, K-major)
+//   * tcgen05.mma (cta_group::1, kind::f16, 128 x BLOCK_N x 16) issued by ONE thread
+//   * fp32 accumulators live in TMEM, double-buffered so the epilogue of tile i overlaps the
+//     main loop of tile i+1
+//   * epilogue warps read TMEM with tcgen05.ld (lane == output row) and fuse
+//     bias / GELU / SwiGLU / residual (+ broadcast "row modulo" residual for position embeddings)
+//
+// Replaces the cuBLAS calls behind nn.Linear on the reference hot path:
+//   SigLIP q/k/v/out_proj, fc1/fc2      (modeling_siglip.py:384-387,707-715)
+//   mm_projector Linear layers          (base_projector.py:145-162)
+//   Qwen2 q/k/v/o, gate/up/down, lm_head (modeling_qwen2.py:164-176,223-226)
+//   patch-embed conv as im2col GEMM     (modeling_siglip.py:269-275,322-328)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vb {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one 128B-swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..5: epilogue
+
+template <int BLOCK_N, int kStages>
+struct GemmSmem {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + align slack
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // gelu_pytorch_tanh: 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  float t = 1.0f - 2.0f / (__expf(2.0f * u) + 1.0f);
+  return 0.5f * x * (1.0f + t);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+template <int BLOCK_N, int kStages>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_w, __nv_bfloat16* __restrict__ C,
+                         int ldc, int M, int N, int K, GemmEpilogue epi) {
+  using S = GemmSmem<BLOCK_N, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * S::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 128);
+    mbar_init(&tmem_empty[1], 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<2 * BLOCK_N>(tmem_ptr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m_blocks;
+        const int n_blk = tile / num_m_blocks;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          tma_load_2d(smem_a + stage * S::kABytes, &tmap_a, &full_bar[stage], kb * BLOCK_K,
+                      m_blk * BLOCK_M);
+          tma_load_2d(smem_b + stage * S::kBBytes, &tmap_w, &full_bar[stage], kb * BLOCK_K,
+                      n_blk * BLOCK_N);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc =
+              make_smem_desc(smem_u32(smem_a + stage * S::kABytes), 16, 1024, kLayoutSW128);
+          const uint64_t b_desc =
+              make_smem_desc(smem_u32(smem_b + stage * S::kBBytes), 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the 128B swizzle atom: +2 in addr>>4 units
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM -> regs -> global) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % num_m_blocks;
+      const int n_blk = tile / num_m_blocks;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N;
+      const __nv_bfloat16* res_row = nullptr;
+      if (epi.residual != nullptr && row_ok) {
+        const int rr = epi.res_row_mod > 0 ? (row % epi.res_row_mod) : row;
+        res_row = epi.residual + static_cast<size_t>(rr) * epi.ld_res;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BLOCK_N + c * 32;
+        if (n0 >= N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (epi.bias != nullptr) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (n0 + g * 8 < N) {
+              const uint4 b = ldg_v4(epi.bias + n0 + g * 8);
+              v[g * 8 + 0] += bf_lo(b.x);
+              v[g * 8 + 1] += bf_hi(b.x);
+              v[g * 8 + 2] += bf_lo(b.y);
+              v[g * 8 + 3] += bf_hi(b.y);
+              v[g * 8 + 4] += bf_lo(b.z);
+              v[g * 8 + 5] += bf_hi(b.z);
+              v[g * 8 + 6] += bf_lo(b.w);
+              v[g * 8 + 7] += bf_hi(b.w);
+            }
+          }
+        }
+        if (epi.swiglu) {
+          // interleaved (gate, up) column pairs -> 16 outputs: silu(gate) * up,
+          // rounding to bf16 at the points the reference's unfused ops do.
+          if (row_ok) {
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float g0 = bf16_round(v[4 * j + 0]), u0 = bf16_round(v[4 * j + 1]);
+              float g1 = bf16_round(v[4 * j + 2]), u1 = bf16_round(v[4 * j + 3]);
+              float a0 = bf16_round(silu_f(g0)) * u0;
+              float a1 = bf16_round(silu_f(g1)) * u1;
+              o[j] = pack_bf16(a0, a1);
+            }
+            __nv_bfloat16* dst = C + static_cast<size_t>(row) * ldc + (n0 >> 1);
+            if (n0 + 16 <= N) stg_v4(dst, make_uint4(o[0], o[1], o[2], o[3]));
+            if (n0 + 32 <= N) stg_v4(dst + 8, make_uint4(o[4], o[5], o[6], o[7]));
+          }
+          continue;
+        }
+        if (epi.act != ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = bf16_round(v[j]);
+            v[j] = epi.act == ACT_GELU_TANH ? gelu_tanh_f(x)
+                                            : (epi.act == ACT_GELU_ERF ? gelu_erf_f(x) : silu_f(x));
+          }
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (n0 + g * 8 < N) {
+              float* w = v + g * 8;
+              if (res_row != nullptr) {
+                const uint4 b = ldg_v4(res_row + n0 + g * 8);
+                w[0] = bf16_round(w[0]) + bf_lo(b.x);
+                w[1] = bf16_round(w[1]) + bf_hi(b.x);
+                w[2] = bf16_round(w[2]) + bf_lo(b.y);
+                w[3] = bf16_round(w[3]) + bf_hi(b.y);
+                w[4] = bf16_round(w[4]) + bf_lo(b.z);
+                w[5] = bf16_round(w[5]) + bf_hi(b.z);
+                w[6] = bf16_round(w[6]) + bf_lo(b.w);
+                w[7] = bf16_round(w[7]) + bf_hi(b.w);
+              }
+              uint4 o;
+              o.x = pack_bf16(w[0], w[1]);
+              o.y = pack_bf16(w[2], w[3]);
+              o.z = pack_bf16(w[4], w[5]);
+              o.w = pack_bf16(w[6], w[7]);
+              stg_v4(C + static_cast<size_t>(row) * ldc + n0 + g * 8, o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BLOCK_N>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, int kStages>
+int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
+                int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
+  using S = GemmSmem<BLOCK_N, kStages>;
+  CUtensorMap ta, tw;
+  if (make_tmap_2d_bf16(&ta, A, M, K, lda, BLOCK_M, BLOCK_K, 128)) return 1;
+  if (make_tmap_2d_bf16(&tw, W, N, K, ldw, BLOCK_N, BLOCK_K, 128)) return 1;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, kStages>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kNumThreads, S::kTotal, stream>>>(ta, tw, C, ldc, M, N, K, epi);
+  VB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
+              int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
+  VB_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  VB_CHECK(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0,
+           "gemm: K, lda, ldw must be multiples of 8 (TMA 16-byte strides): K=%d lda=%d ldw=%d", K,
+           lda, ldw);
+  VB_CHECK(N % 8 == 0 && ldc % 8 == 0, "gemm: N and ldc must be multiples of 8: N=%d ldc=%d", N,
+           ldc);
+  VB_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+           "gemm: pointers must be 16-byte aligned");
+  if (epi.swiglu) VB_CHECK(N % 32 == 0, "gemm: swiglu epilogue needs N %% 32 == 0 (N=%d)", N);
+  // Tile-shape heuristic: keep >= ~1 wave of CTAs; wide tiles when the problem is large.
+  const int sms = num_sms();
+  const int mb = (M + BLOCK_M - 1) / BLOCK_M;
+  const long tiles256 = static_cast<long>(mb) * ((N + 255) / 256);
+  const long tiles128 = static_cast<long>(mb) * ((N + 127) / 128);
+  if (tiles256 >= 2L * sms && N % 256 == 0)
+    return launch_gemm<256, 4>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
+  if (tiles128 >= sms / 2 || N < 128)
+    return launch_gemm<128, 6>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
+  return launch_gemm<64, 8>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
+}
+
+// test hook: force a tile configuration
+int gemm_bf16_cfg(int block_n, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw,
+                  __nv_bfloat16* C, int ldc, int M, int N, int K, const GemmEpilogue& epi,
+                  cudaStream_t stream) {
+  switch (block_n) {
+    case 64: return launch_gemm<64, 8>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
+    case 128: return launch_gemm<128, 6>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
+    case 256: return launch_gemm<256, 4>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
+    default: set_last_error("gemm_bf16_cfg: unsupported block_n %d", block_n); return 1;
+  }
+}
+
+}  // namespace vb
