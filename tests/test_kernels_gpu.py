@@ -1,0 +1,400 @@
+"""Kernel-level parity (GPU): every C-ABI entry point against the oracle's restatement of the
+reference op on the same seeded inputs.  Reference math runs in fp32 on bf16-rounded inputs; the
+tolerance is bf16 output rounding (2^-8 relative) plus accumulation-order noise:
+    max|cuda - ref| <= 1.5e-2 * max|ref|      (stated per test where tighter)
+Integer / pure-permutation kernels must be bit-exact.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import vila_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from vila_b200 import ops
+    return ops
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def rel_err(a, b):
+    return (a.float() - b.float()).abs().max().item() / max(b.float().abs().max().item(), 1e-6)
+
+
+def rb(x):  # round-trip through bf16 (emulate the reference's bf16 tensor between ops)
+    return x.to(torch.bfloat16).float()
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    (128, 128, 64), (256, 256, 128), (1024, 1152, 1152), (280, 3584, 3584), (1000, 4304, 1152),
+    (1024, 1152, 4304), (2048, 1152, 592), (24, 512, 1536), (257, 3584, 4608), (130, 136, 72),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("block_n", [None, 64, 128, 256])
+def test_linear_plain(cuda, M, N, K, block_n):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    x = bf(torch.randn(M, K, device=cuda, generator=g))
+    w = bf(torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K))
+    out = ops.linear(x, w, block_n=block_n)
+    ref = x.float() @ w.float().t()
+    assert rel_err(out, ref) < 8e-3, rel_err(out, ref)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_linear_epilogues(cuda, act, with_res):
+    ops = _ops()
+    M, N, K = 300, 1152, 1152
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = bf(torch.randn(M, K, device=cuda, generator=g))
+    w = bf(torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K))
+    b = bf(torch.randn(N, device=cuda, generator=g))
+    res = bf(torch.randn(M, N, device=cuda, generator=g)) if with_res else None
+    out = ops.linear(x, w, b, act=act, residual=res)
+    ref = rb(x.float() @ w.float().t() + b.float())
+    if act == 1:
+        ref = rb(O.gelu_tanh(ref))
+    elif act == 2:
+        ref = rb(F.gelu(ref))
+    if with_res:
+        ref = rb(ref + res.float())
+    assert rel_err(out, ref) < 1e-2
+
+
+def test_linear_posemb_residual_and_strides(cuda):
+    """patch-embed form: residual row = m % 1024 (position embedding), padded K, strided output."""
+    ops = _ops()
+    M, N, K = 2048, 1152, 592
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = bf(torch.randn(M, K, device=cuda, generator=g))
+    w = bf(torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K))
+    b = bf(torch.randn(N, device=cuda, generator=g))
+    pos = bf(torch.randn(1024, N, device=cuda, generator=g))
+    big = torch.zeros(M, N + 64, dtype=torch.bfloat16, device=cuda)
+    ops.linear(x, w, b, residual=pos, res_row_mod=1024, out=big[:, 32:32 + N])
+    ref = rb(rb(x.float() @ w.float().t() + b.float()) + pos.float().repeat(2, 1))
+    assert rel_err(big[:, 32:32 + N], ref) < 1e-2
+    assert big[:, :32].abs().max() == 0 and big[:, 32 + N:].abs().max() == 0
+
+
+def test_linear_swiglu(cuda):
+    ops = _ops()
+    M, I, K = 280, 2048, 1024
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = bf(torch.randn(M, K, device=cuda, generator=g))
+    wg = bf(torch.randn(I, K, device=cuda, generator=g) / math.sqrt(K))
+    wu = bf(torch.randn(I, K, device=cuda, generator=g) / math.sqrt(K))
+    w = torch.stack([wg, wu], dim=1).reshape(2 * I, K).contiguous()  # interleaved rows
+    out = ops.linear(x, w, swiglu=True)
+    gate = rb(x.float() @ wg.float().t())
+    up = rb(x.float() @ wu.float().t())
+    ref = rb(rb(F.silu(gate)) * up)
+    assert out.shape == (M, I)
+    assert rel_err(out, ref) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# norms
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols", [(1024, 1152), (256, 4608), (7, 13824), (121, 3456)])
+def test_layernorm(cuda, rows, cols):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    x = bf(torch.randn(rows, cols, device=cuda, generator=g) * 3 + 0.5)
+    w = bf(torch.randn(cols, device=cuda, generator=g))
+    b = bf(torch.randn(cols, device=cuda, generator=g))
+    out = ops.layernorm(x, w, b, 1e-6)
+    ref = F.layer_norm(x.float(), (cols,), w.float(), b.float(), 1e-6)
+    assert rel_err(out, ref) < 5e-3
+
+
+@pytest.mark.parametrize("rows,cols", [(280, 3584), (1, 3584), (33, 2048)])
+def test_rmsnorm(cuda, rows, cols):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    x = bf(torch.randn(rows, cols, device=cuda, generator=g) * 2)
+    w = bf(torch.randn(cols, device=cuda, generator=g))
+    out = ops.rmsnorm(x.clone(), w, 1e-6)
+    ref = O.rms_norm(x, w, 1e-6)  # bf16 in, reference rounding points
+    assert rel_err(out, ref) < 1e-6 + 2 ** -7  # at most one bf16 ulp apart
+    assert (out.float() - ref.float()).abs().mean().item() < 1e-4
+    # fused residual add
+    r = bf(torch.randn(rows, cols, device=cuda, generator=g))
+    x2 = x.clone()
+    out2 = ops.rmsnorm(x2, w, 1e-6, residual_add=r)
+    xs = x + r
+    assert torch.equal(x2, xs)
+    assert rel_err(out2, O.rms_norm(xs, w, 1e-6)) < 2 ** -7
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def ref_attention(q, k, v, causal, scale):
+    """q [B,Sq,Hq,D], k/v [B,Sk,Hkv,D] fp32 -> [B,Sq,Hq,D]; softmax fp32, P cast to bf16 (reference)."""
+    B, Sq, Hq, D = q.shape
+    Sk, Hkv = k.shape[1], k.shape[2]
+    rep = Hq // Hkv
+    qq = q.permute(0, 2, 1, 3).float()
+    kk = k.permute(0, 2, 1, 3).float().repeat_interleave(rep, dim=1)
+    vv = v.permute(0, 2, 1, 3).float().repeat_interleave(rep, dim=1)
+    att = qq @ kk.transpose(-1, -2) * scale
+    if causal:
+        mask = torch.ones(Sq, Sk, dtype=torch.bool, device=q.device).tril(Sk - Sq)
+        att = att.masked_fill(~mask, float("-inf"))
+    p = rb(torch.softmax(att, dim=-1))
+    return (p @ vv).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("B,S,H,D", [(2, 1024, 16, 72), (1, 256, 2, 72), (3, 128, 4, 72), (1, 729, 3, 72)])
+def test_fmha_noncausal_siglip(cuda, B, S, H, D):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(B * S + H)
+    qkv = bf(torch.randn(B * S, 3, H, D, device=cuda, generator=g))
+    q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
+    out = ops.fmha(q, k, v, B=B, Sq=S, Sk=S, causal=False, scale=D ** -0.5)
+    ref = ref_attention(q.view(B, S, H, D), k.view(B, S, H, D), v.view(B, S, H, D), False, D ** -0.5)
+    assert rel_err(out.view(B, S, H, D), ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("Sq,Sk,Hq,Hkv", [(280, 280, 28, 4), (128, 128, 4, 4), (1000, 1000, 8, 2),
+                                          (300, 812, 14, 2), (1, 130, 4, 1)])
+def test_fmha_causal_gqa(cuda, Sq, Sk, Hq, Hkv):
+    ops = _ops()
+    D = 128
+    g = torch.Generator(device="cuda").manual_seed(Sq + Sk)
+    q = bf(torch.randn(Sq, Hq, D, device=cuda, generator=g))
+    k = bf(torch.randn(Sk, Hkv, D, device=cuda, generator=g))
+    v = bf(torch.randn(Sk, Hkv, D, device=cuda, generator=g))
+    out = ops.fmha(q, k, v, B=1, Sq=Sq, Sk=Sk, causal=True, scale=D ** -0.5)
+    ref = ref_attention(q[None], k[None], v[None], True, D ** -0.5)[0]
+    assert rel_err(out, ref) < 1.5e-2
+
+
+def test_fmha_paged(cuda):
+    ops = _ops()
+    D, Hq, Hkv, Sq, Sk = 128, 8, 2, 200, 700
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q = bf(torch.randn(Sq, Hq, D, device=cuda, generator=g))
+    k = bf(torch.randn(Sk, Hkv, D, device=cuda, generator=g))
+    v = bf(torch.randn(Sk, Hkv, D, device=cuda, generator=g))
+    n_pages = 16
+    perm = torch.randperm(n_pages, device=cuda, generator=g).to(torch.int32)
+    k_pool = torch.zeros(n_pages, 128, Hkv, D, dtype=torch.bfloat16, device=cuda)
+    v_pool = torch.zeros_like(k_pool)
+    for j in range((Sk + 127) // 128):
+        n = min(128, Sk - j * 128)
+        k_pool[perm[j], :n] = k[j * 128:j * 128 + n]
+        v_pool[perm[j], :n] = v[j * 128:j * 128 + n]
+    out = ops.fmha(q, k_pool, v_pool, B=1, Sq=Sq, Sk=Sk, causal=True, scale=D ** -0.5,
+                   page_table=perm.contiguous())
+    ref = ref_attention(q[None], k[None], v[None], True, D ** -0.5)[0]
+    assert rel_err(out, ref) < 1.5e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# data movement (bit-exact unless averaged)
+# ------------------------------------------------------------------------------------------------
+def test_patch_im2col(cuda):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(12)
+    px = bf(torch.randn(3, 3, 56, 84, device=cuda, generator=g))
+    out = ops.patch_im2col(px, 14, 592)
+    ref = F.unfold(px.float(), kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert torch.equal(out[:, :588].float(), ref)
+    assert out[:, 588:].abs().max() == 0
+
+
+@pytest.mark.parametrize("h,w,r", [(32, 32, 2), (27, 27, 2), (32, 32, 3), (27, 27, 3), (5, 7, 2)])
+def test_space_to_depth(cuda, h, w, r):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(h * w + r)
+    x = bf(torch.randn(2, h * w, 64, device=cuda, generator=g))
+    out = ops.space_to_depth(x, h, w, r)
+    ref = O.flat_square(x.view(2, h, w, 64), r)
+    assert torch.equal(out, ref.reshape(2, -1, ref.shape[-1]))
+
+
+@pytest.mark.parametrize("idx", [-1, 0, 1])
+def test_s2_merge_and_chessboard(cuda, idx):
+    ops = _ops()
+    side, Cc = 4, 16
+    scales = [4, 8, 12]
+    bs = (2, 3)
+    g = torch.Generator(device="cuda").manual_seed(13)
+    tiles = bf(torch.randn(1 + 4 + 6, side * side, Cc, device=cuda, generator=g))
+    feats, nbs = O.merge_features_for_dynamic_s2(tiles, [bs], scales, idx)
+    ref = O.split_chessboard(feats[0], nbs[0][0], nbs[0][1]).flatten(2).transpose(1, 2)
+    out = ops.s2_merge(tiles, [1, 2, bs[0]], [1, 2, bs[1]], nbs[0][0], nbs[0][1])
+    assert out.shape == ref.shape
+    assert (out.float() - ref.float()).abs().max().item() <= 2 ** -7 * ref.float().abs().max().item()
+    # single-tile image (block_size None): features repeated over scales
+    f1, nb1 = O.merge_features_for_dynamic_s2(tiles[:1], [None], scales, idx)
+    ref1 = f1[0].flatten(2).transpose(1, 2)
+    out1 = ops.s2_merge(tiles[:1], [1, 1, 1], [1, 1, 1], 1, 1, share_tile=True)
+    assert torch.equal(out1, ref1)
+    # chessboard merge of projected tiles
+    proj = bf(torch.randn(6, 4, 32, device=cuda, generator=g))
+    refm = O.merge_chessboard(proj, 2, 3)[0].flatten(1).transpose(0, 1)
+    assert torch.equal(ops.chessboard_merge(proj, 2, 3), refm)
+
+
+def test_tsp_pool(cuda):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(14)
+    x = bf(torch.randn(16, 4, 4, 64, device=cuda, generator=g))
+    for ps in [(8, 1, 1), (4, 2, 2), (1, 1, 1)]:
+        ref = x
+        for dim, pp in enumerate(ps):
+            ref = O.tsp_pool(ref, pp, dim)
+        out = ops.tsp_pool(x, *ps)
+        assert (out.float() - ref.float()).abs().max().item() <= 2 ** -7 * ref.float().abs().max().item()
+
+
+def test_embed_splice(cuda):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(15)
+    table = bf(torch.randn(100, 256, device=cuda, generator=g))
+    media = bf(torch.randn(10, 256, device=cuda, generator=g))
+    src = torch.tensor([5, 7, -1, -2, -3, 99, 0, -10], dtype=torch.int32, device=cuda)
+    out = ops.embed_splice(table, media, src)
+    ref = torch.stack([table[s] if s >= 0 else media[-(s + 1)] for s in src.tolist()])
+    assert torch.equal(out, ref)
+
+
+def test_rope_kv_append(cuda):
+    ops = _ops()
+    S, Hq, Hkv, D = 37, 4, 2, 128
+    g = torch.Generator(device="cuda").manual_seed(16)
+    qkv = bf(torch.randn(S, (Hq + 2 * Hkv) * D, device=cuda, generator=g))
+    pos = torch.arange(60000, 60000 + S, dtype=torch.int32, device=cuda)
+    inv = O.rope_inv_freq(D, 1e6).to(cuda)
+    pt = torch.tensor([3, 1], dtype=torch.int32, device=cuda)
+    k_pool = torch.zeros(4, 128, Hkv, D, dtype=torch.bfloat16, device=cuda)
+    v_pool = torch.zeros_like(k_pool)
+    work = qkv.clone()
+    ops.rope_kv_append(work, pos, Hq, Hkv, D, inv, k_pool, v_pool, pt, cache_pos0=100)
+    q = qkv[:, :Hq * D].view(S, Hq, D).transpose(0, 1)
+    k = qkv[:, Hq * D:(Hq + Hkv) * D].view(S, Hkv, D).transpose(0, 1)
+    cos, sin = O.rope_cos_sin(pos.cpu().long(), D, 1e6, torch.bfloat16)
+    qr, kr = O.apply_rope(q, k, cos.to(cuda), sin.to(cuda))
+    got_q = work[:, :Hq * D].view(S, Hq, D).transpose(0, 1)
+    got_k = work[:, Hq * D:(Hq + Hkv) * D].view(S, Hkv, D).transpose(0, 1)
+    assert rel_err(got_q, qr) < 2 ** -6 and rel_err(got_k, kr) < 2 ** -6
+    assert (got_q.float() - qr.float()).abs().mean().item() < 2e-3
+    # cache contents: positions 100..136 -> page pt[0] rows 100..127, page pt[1] rows 0..8
+    v = qkv[:, (Hq + Hkv) * D:].view(S, Hkv, D)
+    assert torch.equal(v_pool[3, 100:128], v[:28]) and torch.equal(v_pool[1, :9], v[28:])
+    assert torch.equal(k_pool[3, 100:128], got_k.transpose(0, 1)[:28])
+
+
+# ------------------------------------------------------------------------------------------------
+# decode kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,K", [(4608, 3584), (3584, 3584), (3584, 18944), (512, 2048), (1000, 1536)])
+def test_gemv_bias_residual_norm(cuda, N, K):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    x = bf(torch.randn(K, device=cuda, generator=g))
+    w = bf(torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K))
+    b = bf(torch.randn(N, device=cuda, generator=g))
+    r = bf(torch.randn(N, device=cuda, generator=g))
+    nw = bf(torch.randn(K, device=cuda, generator=g))
+    out = ops.gemv(x, w, bias=b, residual=r)
+    ref = rb(rb(w.float() @ x.float() + b.float()) + r.float())
+    assert rel_err(out, ref) < 1e-2
+    out = ops.gemv(x, w, norm_w=nw, norm_eps=1e-6)
+    xn = O.rms_norm(x[None], nw, 1e-6)[0]
+    ref = w.float() @ xn.float()
+    assert rel_err(out, ref) < 1e-2
+
+
+def test_gemv_swiglu(cuda):
+    ops = _ops()
+    I, K = 18944, 3584
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = bf(torch.randn(K, device=cuda, generator=g))
+    wg = bf(torch.randn(I, K, device=cuda, generator=g) / math.sqrt(K))
+    wu = bf(torch.randn(I, K, device=cuda, generator=g) / math.sqrt(K))
+    w = torch.stack([wg, wu], dim=1).reshape(2 * I, K).contiguous()
+    out = ops.gemv(x, w, swiglu=True)
+    ref = rb(rb(F.silu(rb(wg.float() @ x.float()))) * rb(wu.float() @ x.float()))
+    assert rel_err(out, ref) < 1e-2
+
+
+def test_gemv_argmax_and_finalize(cuda):
+    ops = _ops()
+    V, K = 152064, 3584
+    g = torch.Generator(device="cuda").manual_seed(22)
+    x = bf(torch.randn(K, device=cuda, generator=g))
+    w = bf(torch.randn(V, K, device=cuda, generator=g) * 0.02)
+    key = torch.zeros(1, dtype=torch.int64, device=cuda)
+    logits = ops.gemv(x, w, argmax_key=key)
+    tok = torch.zeros(1, dtype=torch.int32, device=cuda)
+    hist = torch.zeros(8, dtype=torch.int32, device=cuda)
+    step = torch.zeros(1, dtype=torch.int32, device=cuda)
+    posn = torch.full((1,), 41, dtype=torch.int32, device=cuda)
+    table = bf(torch.randn(V, 64, device=cuda, generator=g))
+    xn = torch.zeros(64, dtype=torch.bfloat16, device=cuda)
+    ops.argmax_finalize(key, tok, hist, step, posn, table, xn)
+    # the kernel's own logits decide (ties -> lowest index, like torch.argmax)
+    expect = int(torch.argmax(logits.float()))
+    assert int(tok) == expect and int(hist[0]) == expect and int(step) == 1 and int(posn) == 42
+    assert int(key) == 0 and torch.equal(xn, table[expect])
+    ref = w.float() @ x.float()
+    assert rel_err(logits, ref) < 1e-2
+    top2 = torch.topk(ref, 2).values
+    if (top2[0] - top2[1]) > 0.05:
+        assert expect == int(torch.argmax(ref))
+
+
+@pytest.mark.parametrize("ctx,splits", [(0, 1), (5, 1), (300, 4), (1000, 8), (130, 16)])
+def test_decode_attention(cuda, ctx, splits):
+    ops = _ops()
+    Hq, Hkv, D = 28, 4, 128
+    g = torch.Generator(device="cuda").manual_seed(ctx + splits)
+    n_pages = 16
+    perm = torch.randperm(n_pages, device=cuda, generator=g).to(torch.int32).contiguous()
+    k_hist = bf(torch.randn(ctx, Hkv, D, device=cuda, generator=g))
+    v_hist = bf(torch.randn(ctx, Hkv, D, device=cuda, generator=g))
+    k_pool = torch.zeros(n_pages, 128, Hkv, D, dtype=torch.bfloat16, device=cuda)
+    v_pool = torch.zeros_like(k_pool)
+    for t in range(ctx):
+        k_pool[perm[t // 128], t % 128] = k_hist[t]
+        v_pool[perm[t // 128], t % 128] = v_hist[t]
+    qkv = bf(torch.randn((Hq + 2 * Hkv) * D, device=cuda, generator=g))
+    pos = torch.tensor([ctx], dtype=torch.int32, device=cuda)
+    inv = O.rope_inv_freq(D, 1e6).to(cuda)
+    out = torch.zeros(Hq * D, dtype=torch.bfloat16, device=cuda)
+    ws = torch.zeros(Hkv * splits * (Hq // Hkv) * (D + 2), dtype=torch.float32, device=cuda)
+    counters = torch.zeros(Hkv, dtype=torch.int32, device=cuda)
+    for _ in range(2):  # twice: counters must re-arm themselves
+        out.zero_()
+        ops.decode_attention(qkv, pos, k_pool, v_pool, perm, out, ws, counters, inv, Hq, Hkv, D,
+                             splits, D ** -0.5)
+    q = qkv[:Hq * D].view(1, Hq, D).transpose(0, 1)
+    kn = qkv[Hq * D:(Hq + Hkv) * D].view(1, Hkv, D).transpose(0, 1)
+    vn = qkv[(Hq + Hkv) * D:].view(1, Hkv, D)
+    cos, sin = O.rope_cos_sin(torch.tensor([ctx]), D, 1e6, torch.bfloat16)
+    qr, kr = O.apply_rope(q, kn, cos.to(cuda), sin.to(cuda))
+    k_all = torch.cat([k_hist, kr.transpose(0, 1)], 0)
+    v_all = torch.cat([v_hist, vn], 0)
+    ref = ref_attention(qr.transpose(0, 1)[None], k_all[None], v_all[None], True, D ** -0.5)[0, 0]
+    assert rel_err(out.view(Hq, D), ref) < 1.5e-2
+    # KV append happened
+    assert torch.equal(k_pool[perm[ctx // 128], ctx % 128], kr.transpose(0, 1)[0])
+    assert torch.equal(v_pool[perm[ctx // 128], ctx % 128], vn[0])
+    assert int(counters.abs().sum()) == 0

@@ -1,0 +1,414 @@
+"""Qwen2 / Llama-style causal LM on the sm_100a kernels (prefill + CUDA-graph decode).
+
+The reference obtains this model from third-party `transformers` (AutoModelForCausalLM,
+llava/model/language_model/builder.py:173-180) and calls `self.llm(inputs_embeds=...)`
+(llava_llama.py:134-141) and `self.llm.generate(inputs_embeds=..., attention_mask=...)`
+(llava_arch.py:833).  This module keeps that surface (`.model.embed_tokens`, `.model.layers`,
+`.model.norm`, `.lm_head`, `.config`, `.vocab_size`, `forward`, `generate`) and the HF state-dict
+names, while q/k/v and gate/up are stored fused (named parameters are views) so each decoder layer is
+  prefill: RMSNorm -> QKV GEMM -> RoPE+KV-append -> tcgen05 FMHA (paged) -> O GEMM(+res)
+           -> RMSNorm -> gate/up GEMM (SwiGLU epilogue) -> down GEMM(+res)
+  decode : [RMSNorm+QKV GEMV] -> [RoPE+append+split-KV attention] -> [O GEMV+res]
+           -> [RMSNorm+gate/up GEMV+SwiGLU] -> [down GEMV+res]      (5 launches, CUDA-graphed)
+Arithmetic spec: in-tree copy llava/eval/vision_niah_vila/zigzag_ring_attn/modeling_qwen2.py
+(RMSNorm :81-95, RoPE :99-160, MLP :164-176, attention :191-310, layer :633-706).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from .. import ops
+from .configuration import Qwen2Config
+
+PAGE = 128
+
+
+def _param(t):
+    return nn.Parameter(t, requires_grad=False)
+
+
+class _Holder(nn.Module):
+    pass
+
+
+class Embedding(nn.Module):
+    """nn.Embedding stand-in whose lookup is the embed_splice gather kernel."""
+
+    def __init__(self, vocab: int, hidden: int, device, dtype):
+        super().__init__()
+        self.weight = _param(torch.empty(vocab, hidden, device=device, dtype=dtype))
+
+    def forward(self, ids: torch.Tensor) -> torch.Tensor:
+        shape = ids.shape
+        src = ids.reshape(-1).to(device=self.weight.device, dtype=torch.int32)
+        return ops.embed_splice(self.weight, None, src).view(*shape, self.weight.shape[1])
+
+
+class Qwen2DecoderLayer(nn.Module):
+    def __init__(self, cfg: Qwen2Config, device, dtype):
+        super().__init__()
+        self.cfg = cfg
+        Hd, I = cfg.hidden_size, cfg.intermediate_size
+        Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        kw = dict(device=device, dtype=dtype)
+        self._qkv_w = torch.empty((Hq + 2 * Hkv) * D, Hd, **kw)
+        self._qkv_b = torch.empty((Hq + 2 * Hkv) * D, **kw)
+        self._gu_w = torch.empty(2 * I, Hd, **kw)  # interleaved rows: gate_0, up_0, gate_1, ...
+        att = _Holder()
+        bounds = {"q_proj": (0, Hq * D), "k_proj": (Hq * D, (Hq + Hkv) * D),
+                  "v_proj": ((Hq + Hkv) * D, (Hq + 2 * Hkv) * D)}
+        for name, (a, b) in bounds.items():
+            lin = _Holder()
+            lin.weight = _param(self._qkv_w[a:b])
+            lin.bias = _param(self._qkv_b[a:b])
+            setattr(att, name, lin)
+        att.o_proj = _Holder()
+        att.o_proj.weight = _param(torch.empty(Hd, Hq * D, **kw))
+        self.self_attn = att
+        mlp = _Holder()
+        mlp.gate_proj = _Holder()
+        mlp.gate_proj.weight = _param(self._gu_w[0::2])
+        mlp.up_proj = _Holder()
+        mlp.up_proj.weight = _param(self._gu_w[1::2])
+        mlp.down_proj = _Holder()
+        mlp.down_proj.weight = _param(torch.empty(Hd, I, **kw))
+        self.mlp = mlp
+        self.input_layernorm = _Holder()
+        self.input_layernorm.weight = _param(torch.empty(Hd, **kw))
+        self.post_attention_layernorm = _Holder()
+        self.post_attention_layernorm.weight = _param(torch.empty(Hd, **kw))
+
+
+class PagedKVCache:
+    """Paged KV pool [L, 2, P, 128, Hkv, D] + page table (DynamicCache replacement)."""
+
+    def __init__(self, cfg: Qwen2Config, max_tokens: int, device, dtype=torch.bfloat16,
+                 page_order: Optional[Sequence[int]] = None):
+        self.n_pages = (max_tokens + PAGE - 1) // PAGE
+        self.pool = torch.zeros(cfg.num_hidden_layers, 2, self.n_pages, PAGE,
+                                cfg.num_key_value_heads, cfg.head_dim, device=device, dtype=dtype)
+        order = list(range(self.n_pages)) if page_order is None else list(page_order)
+        self.page_table = torch.tensor(order, dtype=torch.int32, device=device)
+        self.length = 0
+        self.max_tokens = self.n_pages * PAGE
+
+    def k(self, layer: int) -> torch.Tensor:
+        return self.pool[layer, 0]
+
+    def v(self, layer: int) -> torch.Tensor:
+        return self.pool[layer, 1]
+
+
+class Qwen2ForCausalLM(nn.Module):
+    def __init__(self, cfg: Qwen2Config, device="cuda", dtype=torch.bfloat16):
+        super().__init__()
+        self.config = cfg
+        self.vocab_size = cfg.vocab_size
+        m = _Holder()
+        m.embed_tokens = Embedding(cfg.vocab_size, cfg.hidden_size, device, dtype)
+        m.layers = nn.ModuleList([Qwen2DecoderLayer(cfg, device, dtype)
+                                  for _ in range(cfg.num_hidden_layers)])
+        m.norm = _Holder()
+        m.norm.weight = _param(torch.empty(cfg.hidden_size, device=device, dtype=dtype))
+        self.model = m
+        self.lm_head = _Holder()
+        self.lm_head.weight = _param(torch.empty(cfg.vocab_size, cfg.hidden_size, device=device,
+                                                 dtype=dtype))
+        # HF Qwen2RotaryEmbedding: inv_freq = 1 / theta^(arange(0, D, 2) / D), fp32
+        D = cfg.head_dim
+        self.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))
+                         ).to(device)
+        self.generation_config = None
+        self._decoder = None
+
+    # ---- HF-style accessors ----
+    @property
+    def device(self):
+        return self.lm_head.weight.device
+
+    @property
+    def dtype(self):
+        return self.lm_head.weight.dtype
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    # ---- prefill ----
+    def new_cache(self, max_tokens: int, page_order=None) -> PagedKVCache:
+        return PagedKVCache(self.config, max_tokens, self.device, self.dtype, page_order)
+
+    def prefill_hidden(self, inputs_embeds: torch.Tensor, cache: PagedKVCache,
+                       position_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """inputs_embeds [S, hidden] appended to `cache`; returns the final hidden states [S, hidden]
+        BEFORE the last RMSNorm (the caller norms only the rows it needs)."""
+        cfg = self.config
+        S = inputs_embeds.shape[0]
+        Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        p0 = cache.length
+        assert p0 + S <= cache.max_tokens, "KV cache too small"
+        if position_ids is None:
+            position_ids = torch.arange(p0, p0 + S, dtype=torch.int32, device=self.device)
+        else:
+            position_ids = position_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        x = inputs_embeds.to(self.dtype).contiguous().clone()
+        for li, layer in enumerate(self.model.layers):
+            h = ops.rmsnorm(x, layer.input_layernorm.weight, cfg.rms_norm_eps)
+            qkv = ops.linear(h, layer._qkv_w, layer._qkv_b)
+            ops.rope_kv_append(qkv, position_ids, Hq, Hkv, D, self.inv_freq, cache.k(li),
+                               cache.v(li), cache.page_table, p0)
+            q = qkv.view(S, Hq + 2 * Hkv, D)[:, :Hq]
+            attn = ops.fmha(q, cache.k(li), cache.v(li), B=1, Sq=S, Sk=p0 + S, causal=True,
+                            scale=D ** -0.5, page_table=cache.page_table)
+            ops.linear(attn.view(S, Hq * D), layer.self_attn.o_proj.weight, residual=x, out=x)
+            h = ops.rmsnorm(x, layer.post_attention_layernorm.weight, cfg.rms_norm_eps)
+            a = ops.linear(h, layer._gu_w, swiglu=True)
+            ops.linear(a, layer.mlp.down_proj.weight, residual=x, out=x)
+        cache.length = p0 + S
+        return x
+
+    def logits_from_hidden(self, hidden: torch.Tensor) -> torch.Tensor:
+        """final RMSNorm + lm_head for the given rows [R, hidden] -> [R, V] (bf16 like HF)."""
+        h = ops.rmsnorm(hidden.contiguous().clone(), self.model.norm.weight, self.config.rms_norm_eps)
+        if h.shape[0] == 1:
+            return ops.gemv(h[0], self.lm_head.weight).view(1, -1)
+        return ops.linear(h, self.lm_head.weight)
+
+    def forward(self, inputs_embeds: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None, past_key_values=None, labels=None,
+                use_cache: bool = False, **kw):
+        """Qwen2ForCausalLM.forward(inputs_embeds=[B,S,H]) -> namespace(logits=[B,S,V], loss=None).
+        Padded positions (attention_mask False) are removed before the kernels and returned as 0."""
+        if inputs_embeds.dim() == 2:
+            inputs_embeds = inputs_embeds[None]
+        B, S, _ = inputs_embeds.shape
+        out = torch.zeros(B, S, self.vocab_size, dtype=self.dtype, device=self.device)
+        for b in range(B):
+            emb = inputs_embeds[b]
+            keep = None
+            if attention_mask is not None:
+                keep = attention_mask[b].to(torch.bool)
+                emb = emb[keep]
+            if emb.shape[0] == 0:
+                continue
+            cache = self.new_cache(emb.shape[0])
+            pos = None if position_ids is None else (position_ids[b][keep] if keep is not None
+                                                     else position_ids[b])
+            hid = self.prefill_hidden(emb, cache, pos)
+            lg = self.logits_from_hidden(hid)
+            if keep is None:
+                out[b] = lg
+            else:
+                out[b][keep] = lg
+        loss = None
+        if labels is not None:
+            # training loss is out of scope; provided for API completeness
+            shift_logits = out[:, :-1].float().reshape(-1, self.vocab_size)
+            shift_labels = labels[:, 1:].reshape(-1).to(out.device)
+            loss = torch.nn.functional.cross_entropy(shift_logits, shift_labels, ignore_index=-100)
+        return SimpleNamespace(logits=out, loss=loss, past_key_values=None)
+
+    __call__ = forward
+
+    # ---- decode ----
+    def decoder(self, max_new_tokens: int) -> "GraphDecoder":
+        if self._decoder is None or self._decoder.max_new < max_new_tokens:
+            self._decoder = GraphDecoder(self, max(max_new_tokens, 128))
+        return self._decoder
+
+    @torch.inference_mode()
+    def generate(self, inputs_embeds: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                 generation_config=None, max_new_tokens: Optional[int] = None, do_sample=None,
+                 eos_token_id=None, pad_token_id=None, logits_processor=None, temperature=None,
+                 top_p=None, top_k=None, **kw) -> torch.Tensor:
+        """HF GenerationMixin.generate(inputs_embeds=...) contract: returns ONLY the new ids
+        [B, <=max_new_tokens] (pad-filled after EOS)."""
+        gc = generation_config or self.generation_config
+
+        def pick(name, given, default):
+            if given is not None:
+                return given
+            v = getattr(gc, name, None) if gc is not None else None
+            return default if v is None else v
+
+        max_new = pick("max_new_tokens", max_new_tokens, None)
+        if max_new is None:
+            max_len = pick("max_length", None, 20)
+            max_new = max(1, max_len - inputs_embeds.shape[-2])
+        sample = bool(pick("do_sample", do_sample, False))
+        eos = pick("eos_token_id", eos_token_id, None)
+        eos_ids = [] if eos is None else ([eos] if isinstance(eos, int) else list(eos))
+        pad = pick("pad_token_id", pad_token_id, eos_ids[0] if eos_ids else 0)
+        if inputs_embeds.dim() == 2:
+            inputs_embeds = inputs_embeds[None]
+        outs = []
+        for b in range(inputs_embeds.shape[0]):
+            emb = inputs_embeds[b]
+            if attention_mask is not None:
+                emb = emb[attention_mask[b].to(torch.bool)]
+            if sample or logits_processor:
+                ids = self._generate_eager(emb, max_new, eos_ids, sample, logits_processor,
+                                           pick("temperature", temperature, 1.0),
+                                           pick("top_p", top_p, 1.0), pick("top_k", top_k, 0))
+            else:
+                ids = self._generate_greedy(emb, max_new, eos_ids)
+            outs.append(ids)
+        n = max(len(o) for o in outs)
+        res = torch.full((len(outs), n), pad, dtype=torch.long, device=self.device)
+        for b, o in enumerate(outs):
+            res[b, :len(o)] = torch.tensor(o, dtype=torch.long, device=self.device)
+        return res
+
+    def _generate_greedy(self, emb: torch.Tensor, max_new: int, eos_ids: List[int],
+                         check_every: int = 16) -> List[int]:
+        S = emb.shape[0]
+        dec = self.decoder(max_new)
+        cache = dec.cache_for(S + max_new)
+        hid = self.prefill_hidden(emb, cache)
+        dec.start(hid[-1], cache)
+        done = 0
+        ids: List[int] = []
+        while done < max_new:
+            n = min(check_every, max_new - done)
+            dec.run(n)
+            done += n
+            if eos_ids:
+                ids = dec.tokens(done)
+                hit = [i for i, t in enumerate(ids) if t in eos_ids]
+                if hit:
+                    return ids[:hit[0] + 1]
+        return dec.tokens(done)
+
+    def _generate_eager(self, emb, max_new, eos_ids, sample, processors, temperature, top_p, top_k):
+        """Non-graph path: logits come from the same kernels; the token choice (sampling /
+        logits processors such as xgrammar, llava_arch.py:802-821) is host-side plumbing."""
+        S = emb.shape[0]
+        cache = self.new_cache(S + max_new)
+        hid = self.prefill_hidden(emb, cache)
+        logits = self.logits_from_hidden(hid[-1:])[0]
+        ids: List[int] = []
+        for _ in range(max_new):
+            lg = logits.float()
+            if processors:
+                hist = torch.tensor([ids], dtype=torch.long, device=self.device)
+                for proc in processors:
+                    lg = proc(hist, lg[None])[0]
+            if sample:
+                lg = lg / max(temperature, 1e-5)
+                if top_k and top_k > 0:
+                    kth = torch.topk(lg, top_k).values[-1]
+                    lg = lg.masked_fill(lg < kth, float("-inf"))
+                probs = torch.softmax(lg, -1)
+                if top_p < 1.0:
+                    sp, si = torch.sort(probs, descending=True)
+                    cut = torch.cumsum(sp, 0) - sp > top_p
+                    sp = sp.masked_fill(cut, 0)
+                    probs = torch.zeros_like(probs).scatter(0, si, sp)
+                    probs = probs / probs.sum()
+                tok = int(torch.multinomial(probs, 1))
+            else:
+                tok = int(torch.argmax(lg))
+            ids.append(tok)
+            if tok in eos_ids:
+                break
+            e = self.model.embed_tokens(torch.tensor([tok], device=self.device))
+            hid = self.prefill_hidden(e, cache)
+            logits = self.logits_from_hidden(hid)[0]
+        return ids
+
+
+class GraphDecoder:
+    """Greedy decode loop living entirely on the device: per token 5 launches per layer + lm_head
+    GEMV(argmax) + finalize (token history, position++, next embedding gather), captured in a CUDA
+    graph and replayed without host synchronisation (the reference runs ~400 launches and one D2H
+    stopping-criteria sync per token, SURVEY §3.1 HOT LOOP C)."""
+
+    def __init__(self, llm: Qwen2ForCausalLM, max_new: int, num_splits: int = 8):
+        self.llm = llm
+        cfg = llm.config
+        dev, dt = llm.device, llm.dtype
+        self.max_new = max_new
+        Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        self.num_splits = num_splits
+        self.x = torch.zeros(cfg.hidden_size, device=dev, dtype=dt)
+        self.qkv = torch.zeros((Hq + 2 * Hkv) * D, device=dev, dtype=dt)
+        self.attn = torch.zeros(Hq * D, device=dev, dtype=dt)
+        self.act = torch.zeros(cfg.intermediate_size, device=dev, dtype=dt)
+        self.key = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.token = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.hist = torch.zeros(max_new + 8, device=dev, dtype=torch.int32)
+        self.step = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.position = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.ws = torch.zeros(Hkv * num_splits * (Hq // Hkv) * (D + 2), device=dev,
+                              dtype=torch.float32)
+        self.counters = torch.zeros(Hkv, device=dev, dtype=torch.int32)
+        self.cache: Optional[PagedKVCache] = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 5 * cfg.num_hidden_layers + 2
+
+    def cache_for(self, tokens: int) -> PagedKVCache:
+        """(Re)use a cache big enough; the graph bakes in the pool / page-table pointers."""
+        if self.cache is None or self.cache.max_tokens < tokens:
+            self.cache = self.llm.new_cache(max(tokens, 1024))
+            self.graph = None
+        self.cache.length = 0
+        return self.cache
+
+    def _step(self):
+        llm, cfg, cache = self.llm, self.llm.config, self.cache
+        Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        for li, layer in enumerate(llm.model.layers):
+            ops.gemv(self.x, layer._qkv_w, bias=layer._qkv_b, norm_w=layer.input_layernorm.weight,
+                     norm_eps=cfg.rms_norm_eps, out=self.qkv)
+            ops.decode_attention(self.qkv, self.position, cache.k(li), cache.v(li), cache.page_table,
+                                 self.attn, self.ws, self.counters, llm.inv_freq, Hq, Hkv, D,
+                                 self.num_splits, D ** -0.5)
+            ops.gemv(self.attn, layer.self_attn.o_proj.weight, residual=self.x, out=self.x)
+            ops.gemv(self.x, layer._gu_w, norm_w=layer.post_attention_layernorm.weight,
+                     norm_eps=cfg.rms_norm_eps, swiglu=True, out=self.act)
+            ops.gemv(self.act, layer.mlp.down_proj.weight, residual=self.x, out=self.x)
+        ops.gemv(self.x, llm.lm_head.weight, norm_w=llm.model.norm.weight,
+                 norm_eps=cfg.rms_norm_eps, argmax_key=self.key, write_out=False)
+        ops.argmax_finalize(self.key, self.token, self.hist, self.step, self.position,
+                            llm.model.embed_tokens.weight, self.x)
+
+    def start(self, last_hidden: torch.Tensor, cache: PagedKVCache) -> None:
+        """Seed the loop from the prefill: first new token = argmax(lm_head(norm(last_hidden)))."""
+        assert cache is self.cache
+        llm, cfg = self.llm, self.llm.config
+        self.step.zero_()
+        self.key.zero_()
+        self.position.fill_(cache.length - 1)  # finalize increments -> position of the new token
+        self.x.copy_(last_hidden)
+        ops.gemv(self.x, llm.lm_head.weight, norm_w=llm.model.norm.weight,
+                 norm_eps=cfg.rms_norm_eps, argmax_key=self.key, write_out=False)
+        ops.argmax_finalize(self.key, self.token, self.hist, self.step, self.position,
+                            llm.model.embed_tokens.weight, self.x)
+        self._started = 1
+
+    def run(self, n_tokens: int) -> None:
+        """Produce n_tokens more tokens (the first call's first token already exists from start())."""
+        n = n_tokens
+        if self._started == 1:
+            n -= 1
+            self._started = 2
+        if n <= 0:
+            return
+        if self.graph is None:
+            # warm-up launch outside capture is not allowed to change state: capture directly
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step()
+            self.graph = g
+        for _ in range(n):
+            self.graph.replay()
+        self.cache.length += n
+
+    def tokens(self, n: int) -> List[int]:
+        return self.hist[:n].tolist()
