@@ -1,0 +1,177 @@
+"""Generate tests/golden/*.pt from the REFERENCE's own modules (run once in the authoring container,
+where /root/reference exists; the fixtures are committed so tests never need the reference tree).
+
+Each fixture holds seeded weights (state dict with the reference's names), the synthetic input and the
+output produced by the reference implementation:
+  siglip_tiny.pt     vendored SiglipVisionModel (modeling_siglip.py), hidden_states[-2], sdpa + eager
+  projector_*.pt     reference MultimodalProjector for the three NVILA projector types
+  arch_glue.pt       reference llava_arch.py excerpts (dynamic-S2 encode_images, _embed splice), run
+                     unmodified via ast extraction
+  qwen2_tiny.pt      transformers Qwen2ForCausalLM logits + greedy ids (the reference's LLM is this
+                     third-party class; pinned transformers==4.46.0, here the installed version)
+"""
+from __future__ import annotations
+
+import sys
+import types
+from pathlib import Path
+
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import validate_against_reference as V  # noqa: E402
+from oracle import vila_oracle as O  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+REF = V.REF
+
+
+def half(sd):
+    return {k: v.detach().clone() for k, v in sd.items()}
+
+
+def gen_siglip():
+    import transformers.models.siglip.configuration_siglip as cfgmod
+    ms = V.load_by_path("ref_modeling_siglip", REF / "llava/model/multimodal_encoder/siglip/modeling_siglip.py")
+    torch.manual_seed(100)
+    kw = dict(hidden_size=72, intermediate_size=136, num_hidden_layers=3, num_attention_heads=1,
+              image_size=42, patch_size=14)
+    cfg = cfgmod.SiglipVisionConfig(**kw)
+    cfg._attn_implementation = "sdpa"
+    model = ms.SiglipVisionModel(cfg).eval()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.1)
+                if "layer_norm" in n and n.endswith("weight"):
+                    p.add_(1.0)
+    px = torch.randn(2, 3, 42, 42)
+    with torch.no_grad():
+        hs = model(px, output_hidden_states=True).hidden_states
+    sd = {k: v for k, v in model.state_dict().items() if ".head." not in k}
+    torch.save({"cfg": kw, "weights": half(sd), "pixels": px, "hidden_m2": hs[-2], "hidden_m1": hs[-1],
+                "n_hidden_states": len(hs)}, OUT / "siglip_tiny.pt")
+
+
+def gen_projector():
+    import transformers  # noqa: F401
+    timm = types.ModuleType("timm"); timm_m = types.ModuleType("timm.models")
+    timm_l = types.ModuleType("timm.models.layers"); timm_l.Mlp = type("Mlp", (torch.nn.Module,), {})
+    sys.modules.setdefault("timm", timm); sys.modules.setdefault("timm.models", timm_m)
+    sys.modules.setdefault("timm.models.layers", timm_l)
+    bp = V.load_by_path("refprojector", REF / "llava/model/multimodal_projector/base_projector.py")
+    torch.manual_seed(101)
+    out = {}
+    for kind, n_tok in (("mlp_downsample", 49), ("mlp_downsample_2x2_fix", 64), ("mlp_downsample_3x3_fix", 64)):
+        cfg = types.SimpleNamespace(mm_hidden_size=24, hidden_size=40)
+        model = bp.MultimodalProjector(bp.MultimodalProjectorConfig(kind), cfg).eval()
+        with torch.no_grad():
+            for p in model.parameters():
+                if p.dim() == 1:
+                    p.normal_(0, 0.2)
+        x = torch.randn(2, n_tok, 24)
+        with torch.no_grad():
+            y = model(x)
+        out[kind] = {"weights": half(model.state_dict()), "x": x, "y": y}
+    torch.save(out, OUT / "projector.pt")
+
+
+def gen_arch_glue():
+    from collections import defaultdict, deque
+    from einops import rearrange
+    import textwrap
+    names = ["merge_chessboard", "split_chessboard", "merge_features_for_dynamic_s2", "encode_images",
+             "_embed", "__embed_media_tokens", "__truncate_sequence", "__batchify_sequence"]
+    srcs = V.extract_functions(REF / "llava/model/llava_arch.py", names)
+    ns = {"torch": torch, "F": F, "rearrange": rearrange, "Optional": object, "Tuple": object,
+          "Dict": dict, "List": list, "Any": object, "deque": deque, "defaultdict": defaultdict,
+          "IGNORE_INDEX": -100, "get_pg_manager": lambda: None, "warnings": __import__("warnings"),
+          "chain": __import__("itertools").chain, "distributed": None}
+    body = "class RefArch:\n"
+    for n in names:
+        s = srcs[n].replace("@staticmethod\n", "")
+        body += textwrap.indent(("@staticmethod\n" if n in ("merge_chessboard", "split_chessboard") else "") + s, "    ") + "\n"
+    exec(compile(body, "<reference llava_arch excerpts>", "exec"), ns)
+    RefArch = ns["RefArch"]
+    torch.manual_seed(102)
+    C_, side = 8, 4
+    lin_w, lin_b = torch.randn(16, 3 * 4 * C_) * 0.1, torch.randn(16) * 0.1
+    fixtures = {"lin_w": lin_w, "lin_b": lin_b, "s2": []}
+    for idx in (-1, 0, 1):
+        tower = types.SimpleNamespace(scales=[4, 8, 12], resize_output_to_scale_idx=idx)
+        tower_fn = lambda images: images
+        proj = lambda f: F.linear(O.downsample(f, 2), lin_w, lin_b)
+        self_ = RefArch()
+        self_.config = types.SimpleNamespace(dynamic_s2=True)
+        tower_obj = type("T", (), {"scales": [4, 8, 12], "resize_output_to_scale_idx": idx,
+                                   "__call__": lambda s, im: im})()
+        self_.get_vision_tower = lambda t=tower_obj: t
+        self_.get_mm_projector = lambda: proj
+        block_sizes = [(2, 3), None, (1, 2)]
+        n_tiles = (1 + 4 + 6) + 1 + (1 + 4 + 2)
+        feats = torch.randn(n_tiles, side * side, C_)
+        with torch.no_grad():
+            ref = self_.encode_images(feats, block_sizes)
+        fixtures["s2"].append({"idx": idx, "block_sizes": block_sizes, "feats": feats,
+                               "out": [r.clone() for r in ref]})
+    # _embed
+    V_, H = 50, 8
+    table = torch.randn(V_, H)
+    self_ = RefArch()
+    self_.training = False
+    self_.llm = types.SimpleNamespace(model=types.SimpleNamespace(embed_tokens=lambda ids: F.embedding(ids, table)))
+    IMG, VID = 40, 41
+    self_.tokenizer = types.SimpleNamespace(media_token_ids={"image": IMG, "video": VID},
+                                            padding_side="right", model_max_length=4096)
+    m_img = [torch.randn(5, H), torch.randn(3, H)]
+    m_vid = [torch.randn(7, H)]
+    self_.encoders = {"image": lambda media, cfg: list(media), "video": lambda media, cfg: list(media)}
+    ids = torch.tensor([[1, 2, IMG, 3, VID, 4, 0, 0], [IMG, 9, 8, 7, 6, 5, 4, 3]])
+    am = torch.tensor([[1, 1, 1, 1, 1, 1, 0, 0], [1, 1, 1, 1, 1, 1, 1, 1]], dtype=torch.bool)
+    emb = {}
+    for side_ in ("right", "left"):
+        self_.tokenizer.padding_side = side_
+        a, b, c = getattr(self_, "_embed")(ids, {"image": list(m_img), "video": list(m_vid)},
+                                           {"image": {}, "video": {}}, None, am)
+        emb[side_] = {"inputs": a, "labels": b, "mask": c}
+    fixtures["embed"] = {"table": table, "ids": ids, "mask": am, "m_img": m_img, "m_vid": m_vid,
+                         "IMG": IMG, "VID": VID, "out": emb}
+    torch.save(fixtures, OUT / "arch_glue.pt")
+
+
+def gen_qwen2():
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    torch.manual_seed(103)
+    kw = dict(hidden_size=64, intermediate_size=160, num_hidden_layers=2, num_attention_heads=4,
+              num_key_value_heads=2, vocab_size=256, rms_norm_eps=1e-6, rope_theta=1000000.0)
+    hcfg = Qwen2Config(max_position_embeddings=4096, tie_word_embeddings=False,
+                       attn_implementation="sdpa", **kw)
+    model = Qwen2ForCausalLM(hcfg).eval()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "norm" in n:
+                p.normal_(1.0, 0.1)
+            elif p.dim() == 1:
+                p.normal_(0, 0.1)
+    emb = torch.randn(1, 21, 64)
+    pos = torch.arange(30000, 30021)
+    with torch.no_grad():
+        logits = model(inputs_embeds=emb).logits[0]
+        logits_far = model(inputs_embeds=emb, position_ids=pos[None]).logits[0]
+        gen = model.generate(inputs_embeds=emb, attention_mask=torch.ones(1, 21, dtype=torch.long),
+                             max_new_tokens=10, do_sample=False, eos_token_id=None, pad_token_id=0)
+    torch.save({"cfg": kw, "weights": half(model.state_dict()), "emb": emb, "logits": logits,
+                "pos_far": pos, "logits_far": logits_far, "greedy": gen[0].tolist(),
+                "transformers_version": __import__("transformers").__version__},
+               OUT / "qwen2_tiny.pt")
+
+
+if __name__ == "__main__":
+    assert REF.exists(), "needs /root/reference"
+    OUT.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(4)
+    gen_siglip(); gen_projector(); gen_arch_glue(); gen_qwen2()
+    for f in sorted(OUT.glob("*.pt")):
+        print(f.name, f.stat().st_size)

@@ -1,0 +1,183 @@
+"""End-to-end parity (GPU): vila_b200.model.LlavaLlamaModel through its public API against the CPU
+oracle on identical random-init weights and synthetic inputs.  Tolerance model: tests/helpers.py
+(check_close): CUDA error vs fp32 truth <= 2x the reference's own bf16 error + 1e-3 relative;
+greedy ids exact up to the first bf16-level tie."""
+import pytest
+import torch
+
+from tests.helpers import check_close, greedy_ids_match, oracle_from_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def build(cfg, seed=0):
+    from vila_b200.model import LlavaLlamaModel
+    return LlavaLlamaModel(cfg, device="cuda").init_random(seed)
+
+
+def synth_inputs(cfg, n_images=1, n_text=9, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    S = cfg.vision_tower_cfg.image_size
+    images = [torch.randn(3, S, S, generator=g).to(torch.bfloat16) for _ in range(n_images)]
+    ids = torch.randint(3, 900, (n_text,), generator=g).tolist()
+    for k in range(n_images):
+        ids.insert(2 + 3 * k, cfg.image_token_id)
+    return torch.tensor([ids]), images
+
+
+@pytest.mark.parametrize("projector", ["mlp_downsample", "mlp_downsample_2x2_fix", "mlp_downsample_3x3_fix"])
+def test_forward_logits_match_oracle(cuda, projector):
+    from vila_b200.model import tiny_test_config
+    cfg = tiny_test_config(projector=projector)
+    model = build(cfg)
+    ids, images = synth_inputs(cfg, n_images=2)
+    out = model(input_ids=ids, media={"image": [im.cuda() for im in images]})
+    sd = model.state_dict()
+    truth = oracle_from_state_dict(sd, cfg, torch.float32).forward_logits(
+        ids, [im.float() for im in images])
+    lowp = oracle_from_state_dict(sd, cfg, torch.bfloat16).forward_logits(ids, images)
+    assert out.logits.shape[1] == truth.shape[0]
+    check_close(f"logits[{projector}]", out.logits[0], truth, lowp)
+
+
+def test_vision_tower_and_projector_stages(cuda):
+    from vila_b200.model import tiny_test_config
+    cfg = tiny_test_config(vis_layers=4)
+    model = build(cfg, seed=3)
+    _, images = synth_inputs(cfg, n_images=3)
+    px = torch.stack(images).cuda()
+    sd = model.state_dict()
+    o32 = oracle_from_state_dict(sd, cfg, torch.float32)
+    o16 = oracle_from_state_dict(sd, cfg, torch.bfloat16)
+    feats = model.vision_tower(px)
+    t32 = o32.tower(torch.stack(images).float())
+    check_close("vision_tower", feats, t32, o16.tower(torch.stack(images)))
+    enc = model.encode_images(px)
+    check_close("encode_images", enc, o32.project(t32), o16.encode_images(torch.stack(images)))
+    # list input and fp16 input (reference calls .half() on pixels, llava_arch.py:864)
+    lst = model.vision_tower([im.cuda() for im in images])
+    assert torch.equal(torch.stack(lst), feats)
+    assert model.vision_tower(px.half()).dtype == torch.float16
+
+
+@pytest.mark.parametrize("idx", [-1, 0])
+def test_encode_images_dynamic_s2(cuda, idx):
+    from vila_b200.model import tiny_test_config
+    cfg = tiny_test_config(dynamic_s2=True, image_size=56, s2_resize_output_to_scale_idx=idx)
+    model = build(cfg, seed=4)
+    g = torch.Generator().manual_seed(5)
+    block_sizes = [(2, 3), None, (1, 2)]
+    n_tiles = (1 + 4 + 6) + 1 + (1 + 4 + 2)
+    px = torch.randn(n_tiles, 3, 56, 56, generator=g).to(torch.bfloat16)
+    got = model.encode_images(px.cuda(), block_sizes=block_sizes)
+    sd = model.state_dict()
+    t32 = oracle_from_state_dict(sd, cfg, torch.float32).encode_images(px.float(), block_sizes)
+    t16 = oracle_from_state_dict(sd, cfg, torch.bfloat16).encode_images(px, block_sizes)
+    assert len(got) == len(t32) == 3
+    for i, (a, b, c) in enumerate(zip(got, t32, t16)):
+        assert a.shape == b.shape
+        check_close(f"dynamic_s2 image {i}", a, b, c)
+
+
+def test_generate_greedy_matches_oracle(cuda):
+    from vila_b200.model import tiny_test_config
+    cfg = tiny_test_config(llm_layers=3)
+    model = build(cfg, seed=6)
+    ids, images = synth_inputs(cfg, n_images=1, n_text=12)
+    out = model.generate(input_ids=ids, media={"image": [images[0].cuda()]}, max_new_tokens=24,
+                         eos_token_id=None)
+    assert out.shape == (1, 24) and out.dtype == torch.long
+    oracle = oracle_from_state_dict(model.state_dict(), cfg, torch.float32)
+    want, logits = oracle.generate(ids, [images[0].float()], 24)
+    # margin: 3 bf16 ulps at the logit scale
+    margin = 3 * 2 ** -8 * logits.abs().max().item()
+    greedy_ids_match(out[0].tolist(), want, logits, margin)
+    # eos handling: stop right after the first generated token when it is declared EOS
+    first = int(out[0, 0])
+    out2 = model.generate(input_ids=ids, media={"image": [images[0].cuda()]}, max_new_tokens=24,
+                          eos_token_id=[first])
+    assert out2.tolist() == [[first]]
+    # second call reuses the captured CUDA graph and must reproduce the same ids
+    out3 = model.generate(input_ids=ids, media={"image": [images[0].cuda()]}, max_new_tokens=24,
+                          eos_token_id=None)
+    assert torch.equal(out, out3)
+
+
+def test_decode_logits_match_prefill(cuda):
+    """KV-cached decode (GEMV + split-KV attention path) must agree with re-running the prefill
+    (GEMM + FMHA path) on the extended sequence."""
+    from vila_b200.model import tiny_test_config
+    cfg = tiny_test_config(llm_layers=2)
+    model = build(cfg, seed=7)
+    llm = model.llm
+    g = torch.Generator(device="cuda").manual_seed(8)
+    emb = (torch.randn(150, cfg.hidden_size, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    cache = llm.new_cache(256)
+    hid = llm.prefill_hidden(emb[:140], cache)
+    lg_a = None
+    for t in range(140, 150):  # extend token by token through the prefill path with Sq=1
+        hid = llm.prefill_hidden(emb[t:t + 1], cache)
+    lg_a = llm.logits_from_hidden(hid[-1:])
+    cache2 = llm.new_cache(256)
+    hid2 = llm.prefill_hidden(emb, cache2)
+    lg_b = llm.logits_from_hidden(hid2[-1:])
+    check_close("incremental vs full prefill", lg_a, lg_b.float())
+
+
+def test_batch_padding_and_video_encoders(cuda):
+    from vila_b200.model import tiny_test_config
+    from oracle import vila_oracle as O
+    cfg = tiny_test_config(projector="mlp_downsample_2x2_fix", video_encoder="tsp",
+                           tsp_pool_sizes=((4, 1, 1), (2, 2, 2)))
+    model = build(cfg, seed=9)
+    g = torch.Generator().manual_seed(10)
+    S = cfg.vision_tower_cfg.image_size
+    video = torch.randn(8, 3, S, S, generator=g).to(torch.bfloat16)
+    image = torch.randn(3, S, S, generator=g).to(torch.bfloat16)
+    ids = torch.tensor([[5, cfg.video_token_id, 6, 7, cfg.image_token_id, 8],
+                        [9, 10, 11, cfg.pad_token_id, cfg.pad_token_id, cfg.pad_token_id]])
+    mask = torch.tensor([[1, 1, 1, 1, 1, 1], [1, 1, 1, 0, 0, 0]], dtype=torch.bool)
+    emb, labels, amask = model._embed(ids, {"video": [video.cuda()], "image": [image.cuda()]},
+                                      {"video": {}, "image": {}}, None, mask)
+    sd = model.state_dict()
+    o32 = oracle_from_state_dict(sd, cfg, torch.float32)
+    feats_v = o32.encode_images(video.float())
+    feats_i = o32.encode_images(image.float()[None])
+    end = o32.llm["model.embed_tokens.weight"][list(cfg.newline_token_ids)]
+    vid = O.tsp_video_encoder(feats_v, cfg.tsp_pool_sizes, end)
+    img = O.image_encoder(list(feats_i), end)
+    want, wlab, wmask = O.embed_splice(ids, o32.llm["model.embed_tokens.weight"],
+                                       {"video": [vid], "image": img},
+                                       {"image": cfg.image_token_id, "video": cfg.video_token_id},
+                                       None, mask, "right")
+    assert emb.shape == want.shape
+    assert torch.equal(amask.cpu(), wmask) and torch.equal(labels.cpu(), wlab)
+    check_close("_embed (video TSP + image, padded batch)", emb, want)
+    # forward over the padded batch returns zeros on padded positions
+    out = model(input_ids=ids, media={"video": [video.cuda()], "image": [image.cuda()]}, attention_mask=mask)
+    assert out.logits.shape[:2] == want.shape[:2]
+    assert out.logits[1, 3:].abs().max().item() == 0
+    with pytest.raises(ValueError):
+        model._embed(ids[:1, :1], {"image": [image.cuda()]}, {"image": {}}, None, None)
+
+
+def test_save_load_roundtrip(cuda, tmp_path):
+    from vila_b200.model import tiny_test_config
+    from vila_b200.model.loading import load_pretrained, save_pretrained
+    cfg = tiny_test_config()
+    model = build(cfg, seed=11)
+    save_pretrained(model, str(tmp_path / "ckpt"))
+    again = load_pretrained(str(tmp_path / "ckpt"))
+    a, b = model.state_dict(), again.state_dict()
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    ids, images = synth_inputs(cfg)
+    la = model(input_ids=ids, media={"image": [images[0].cuda()]}).logits
+    lb = again(input_ids=ids, media={"image": [images[0].cuda()]}).logits
+    assert torch.equal(la, lb)
+
+
+def test_no_cpu_fallback(cuda):
+    """The product path must fail loudly on CPU tensors instead of silently computing elsewhere."""
+    from vila_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.linear(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))

@@ -100,7 +100,12 @@ def load() -> C.CDLL:
     return lib
 
 
+LAUNCHES = 0  # number of C-ABI compute calls issued from this process (bench.py reports it)
+
+
 def check(rc: int, what: str) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         msg = load().vila_last_error()
         raise RuntimeError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

@@ -106,7 +106,10 @@ class BasicImageEncoder(BaseEncoder):
         return torch.cat(parts, dim=0) if len(parts) > 1 else features
 
     def forward(self, images: List[torch.Tensor], config: Dict[str, Any], **kw) -> List[torch.Tensor]:
-        images = torch.stack(images, dim=0)
+        # host tensors (pinned by the caller) are copied H2D asynchronously BEFORE stacking so the
+        # copy stays a pinned-memory DMA; the reference stacks on the host then moves the batch.
+        dev = self.parent.device
+        images = torch.stack([im.to(dev, non_blocking=True) for im in images], dim=0)
         features = self.parent.encode_images(images, block_sizes=config.get("block_sizes"))
         s, e = self.embed_tokens(self.start_tokens), self.embed_tokens(self.end_tokens)
         return [self._process_features(f, s, e) for f in features]
@@ -218,14 +221,22 @@ class LlavaLlamaModel(nn.Module):
 
     # ---- weights ----
     @torch.no_grad()
-    def init_random(self, seed: int = 0) -> "LlavaLlamaModel":
+    def init_random(self, seed: int = 0, device_rng: bool = False) -> "LlavaLlamaModel":
         """Random init of the named architecture (no checkpoints / network here): HF Qwen2 init
         (normal 0.02, norms 1), SigLIP _init_weights (modeling_siglip.py:786-825: xavier-uniform
         attention/MLP weights, position embedding std 1/sqrt(width)), default nn.Linear init for the
         projector.  Biases / LN params get small non-zero noise so that parity tests exercise them."""
         g = torch.Generator(device="cpu").manual_seed(seed)
+        gd = torch.Generator(device=self.device).manual_seed(seed) if device_rng else None
 
         def fill(p: torch.Tensor, std: float, mean: float = 0.0):
+            if gd is not None:  # fast path for the 8B-scale benchmark model (device RNG)
+                rows = p.shape[0]
+                step = max(1, (1 << 28) // max(1, p.numel() // rows))
+                for r in range(0, rows, step):
+                    blk = p[r:r + step]
+                    blk.copy_((torch.randn(blk.shape, generator=gd, device=p.device) * std + mean).to(p.dtype))
+                return
             # generate on the CPU for device-independent reproducibility, in chunks to bound memory
             flat_n = p.numel()
             if flat_n <= 1 << 26:

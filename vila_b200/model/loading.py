@@ -1,0 +1,107 @@
+"""Checkpoint IO in the reference's three-directory layout (llava_arch.py:158-204; resolved at load
+by llava/model/utils/utils.py:25-55):
+
+    <model_dir>/config.json                (top-level LlavaConfig fields)
+    <model_dir>/llm/{config.json,*.safetensors}
+    <model_dir>/vision_tower/{config.json,*.safetensors}
+    <model_dir>/mm_projector/{config.json,*.safetensors}
+
+State-dict prefixes inside the sub-directories follow HF: `model.*` / `lm_head.*` for the LLM,
+`vision_model.*` for SigLIP, `layers.*` for the projector.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Dict
+
+import torch
+
+from .configuration import LlavaConfig, Qwen2Config, SiglipVisionConfig
+from .llava_llama import LlavaLlamaModel
+
+
+def _load_dir_tensors(d: Path) -> Dict[str, torch.Tensor]:
+    from safetensors.torch import load_file
+
+    out: Dict[str, torch.Tensor] = {}
+    files = sorted(d.glob("*.safetensors"))
+    if not files:
+        bins = sorted(d.glob("*.bin"))
+        for b in bins:
+            out.update(torch.load(b, map_location="cpu", weights_only=True))
+        return out
+    for f in files:
+        out.update(load_file(str(f)))
+    return out
+
+
+def _pick(cfg: dict, cls):
+    fields = {f for f in cls.__dataclass_fields__}
+    return cls(**{k: v for k, v in cfg.items() if k in fields})
+
+
+def config_from_dir(model_dir: Path) -> LlavaConfig:
+    top = json.loads((model_dir / "config.json").read_text())
+    llm = _pick(json.loads((model_dir / "llm" / "config.json").read_text()), Qwen2Config)
+    vis_raw = json.loads((model_dir / "vision_tower" / "config.json").read_text())
+    vis = _pick(vis_raw.get("vision_config", vis_raw), SiglipVisionConfig)
+    proj = json.loads((model_dir / "mm_projector" / "config.json").read_text())
+    kw = {}
+    for k in ("mm_vision_select_layer", "mm_vision_select_feature", "image_aspect_ratio", "dynamic_s2",
+              "s2_max_split_size", "s2_resize_output_to_scale_idx", "num_video_frames"):
+        if k in top and top[k] is not None:
+            kw[k] = top[k]
+    if top.get("s2_scales"):
+        s = top["s2_scales"]
+        kw["s2_scales"] = tuple(int(x) for x in (s.split(",") if isinstance(s, str) else s))
+    return LlavaConfig(llm_cfg=llm, vision_tower_cfg=vis,
+                       mm_projector_type=proj.get("mm_projector_type", "mlp_downsample"), **kw)
+
+
+def load_pretrained(model_path: str, device="cuda") -> LlavaLlamaModel:
+    d = Path(model_path)
+    cfg = config_from_dir(d)
+    tok = None
+    try:  # a real checkpoint ships the tokenizer next to the LLM
+        from transformers import AutoTokenizer
+        tok = AutoTokenizer.from_pretrained(str(d / "llm"))
+        tok.media_token_ids = {"image": tok.convert_tokens_to_ids("<image>"),
+                               "video": tok.convert_tokens_to_ids("<vila/video>")}
+        tok.stop_token_ids = [tok.eos_token_id]
+    except Exception:
+        tok = None
+    model = LlavaLlamaModel(cfg, device=device, tokenizer=tok)
+    sd = {}
+    sd.update({"llm." + k: v for k, v in _load_dir_tensors(d / "llm").items()})
+    sd.update({"vision_tower.vision_tower." + k: v for k, v in _load_dir_tensors(d / "vision_tower").items()})
+    sd.update({"mm_projector." + k: v for k, v in _load_dir_tensors(d / "mm_projector").items()})
+    own = model.state_dict()
+    missing = [k for k in own if k not in sd]
+    if missing:
+        raise RuntimeError(f"checkpoint {model_path} lacks {len(missing)} tensors, e.g. {missing[:4]}")
+    with torch.no_grad():
+        for k, p in own.items():
+            p.copy_(sd[k].to(p.dtype))
+    return model
+
+
+def save_pretrained(model: LlavaLlamaModel, model_path: str) -> None:
+    from dataclasses import asdict
+
+    from safetensors.torch import save_file
+
+    d = Path(model_path)
+    parts = {"llm": "llm.", "vision_tower": "vision_tower.vision_tower.", "mm_projector": "mm_projector."}
+    sd = model.state_dict()
+    for sub, prefix in parts.items():
+        (d / sub).mkdir(parents=True, exist_ok=True)
+        tensors = {k[len(prefix):]: v.detach().cpu().contiguous() for k, v in sd.items()
+                   if k.startswith(prefix)}
+        save_file(tensors, str(d / sub / "model.safetensors"))
+    (d / "llm" / "config.json").write_text(json.dumps(asdict(model.config.llm_cfg)))
+    (d / "vision_tower" / "config.json").write_text(json.dumps(asdict(model.config.vision_tower_cfg)))
+    (d / "mm_projector" / "config.json").write_text(
+        json.dumps({"mm_projector_type": model.config.mm_projector_type}))
+    top = {k: v for k, v in model.config.to_dict().items() if k not in ("llm_cfg", "vision_tower_cfg")}
+    (d / "config.json").write_text(json.dumps(top))
