@@ -1,0 +1,100 @@
+"""CPU / gloo (world_size 2 and 4): host logic of the sequence-parallel prefill — zigzag partition,
+page-table permutation and the in-place all-gather layout — without any GPU kernel."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vila_b200 import sp
+
+
+def test_plan_matches_reference_zigzag():
+    """prepare_zigzag_ring_attn_inputs / extract_local (zigzag_ring_attn/prepare_inputs.py:20-23):
+    value.chunk(2*world)[rank] ++ value.chunk(2*world)[2*world-1-rank]."""
+    for world in (1, 2, 4, 8):
+        S = 2 * world * 128 * 3
+        x = torch.arange(S)
+        for rank in range(world):
+            plan = sp.make_plan(S, world, rank)
+            chunks = x.chunk(2 * world)
+            want = torch.cat([chunks[rank], chunks[2 * world - 1 - rank]])
+            assert torch.equal(plan.extract_local(x), want)
+            assert torch.equal(plan.local_positions().long(), want)
+
+
+def test_padding_and_ownership():
+    plan = sp.make_plan(65800, 8, 3)
+    assert plan.padded_len % (16 * 128) == 0 and plan.padded_len >= 65800
+    assert plan.padded_len - 65800 < 16 * 128
+    assert plan.chunk % 128 == 0
+    last_owner = plan.owner_of(plan.padded_len - 1)
+    assert last_owner == 0  # the last chunk (2P-1) belongs to rank 0
+    # causal work is balanced: sum over a rank's two chunks of the KV length they attend to
+    work = []
+    for r in range(8):
+        work.append(sum(e for _, e in plan.local_chunks(r)))
+    assert max(work) == min(work)
+    # frame sharding covers all frames exactly once
+    spans = [sp.shard_frames(250, 8, r) for r in range(8)]
+    assert spans[0][0] == 0 and spans[-1][1] == 250
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(7))
+
+
+def test_page_table_is_a_permutation_and_undo():
+    for world in (2, 4):
+        S = 2 * world * 128 * 2
+        tables = sp.make_plan(S, world, 0).page_table()
+        assert sorted(tables.tolist()) == list(range(S // 128))
+        plan = sp.make_plan(S, world, 1)
+        x = torch.randn(S, 3)
+        gathered = torch.stack([plan.extract_local(x, r) for r in range(world)])
+        assert torch.equal(plan.undo_extract_local(gathered), x)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, S, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        Hkv, D = 2, 4
+        plan = sp.make_plan(S, world, rank)
+        g = torch.Generator().manual_seed(0)
+        kv_global = torch.randn(plan.padded_len, Hkv, D, generator=g)  # same on every rank
+        pool = torch.zeros(plan.padded_len // 128, 128, Hkv, D)
+        pt = plan.page_table()
+        # each rank writes ONLY its own tokens through the page table (what rope_kv_append does)
+        for pos in plan.local_positions().tolist():
+            pool[pt[pos // 128], pos % 128] = kv_global[pos]
+        n_local = 2 * plan.chunk_pages
+        lo = rank * n_local
+        # pages written so far must all lie inside this rank's all-gather region
+        touched = pool.abs().sum(dim=(1, 2, 3)) > 0
+        assert touched[lo:lo + n_local].all() and int(touched.sum()) == n_local
+        dist.all_gather_into_tensor(pool.view(-1), pool[lo:lo + n_local].clone().view(-1))
+        # reading block j through the page table now yields the global order on every rank
+        rebuilt = torch.cat([pool[pt[j]] for j in range(plan.padded_len // 128)])
+        ok = torch.equal(rebuilt, kv_global)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_inplace_allgather_into_paged_pool_gloo(world):
+    S = 2 * world * 128 * 2 - 77  # not a multiple: exercises padding
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, S, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)

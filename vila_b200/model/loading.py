@@ -49,9 +49,15 @@ def config_from_dir(model_dir: Path) -> LlavaConfig:
     proj = json.loads((model_dir / "mm_projector" / "config.json").read_text())
     kw = {}
     for k in ("mm_vision_select_layer", "mm_vision_select_feature", "image_aspect_ratio", "dynamic_s2",
-              "s2_max_split_size", "s2_resize_output_to_scale_idx", "num_video_frames"):
+              "s2_max_split_size", "s2_resize_output_to_scale_idx", "num_video_frames", "video_encoder",
+              "model_max_length", "image_token_id", "video_token_id", "pad_token_id"):
         if k in top and top[k] is not None:
             kw[k] = top[k]
+    for k in ("newline_token_ids", "eos_token_ids"):
+        if top.get(k) is not None:
+            kw[k] = tuple(top[k])
+    if top.get("tsp_pool_sizes") is not None:
+        kw["tsp_pool_sizes"] = tuple(tuple(p) for p in top["tsp_pool_sizes"])
     if top.get("s2_scales"):
         s = top["s2_scales"]
         kw["s2_scales"] = tuple(int(x) for x in (s.split(",") if isinstance(s, str) else s))
