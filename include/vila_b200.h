@@ -31,16 +31,32 @@ extern "C" {
 #define VILA_ACT_GELU_ERF 2  /* nn.GELU() in mm_projector   (base_projector.py:145-162)  */
 #define VILA_ACT_SILU 3
 
+/* `flags` of vila_linear / vila_gemv:
+ *   VILA_FLAG_SWIGLU    weight rows are interleaved (gate_0, up_0, gate_1, ...); out is [M, N/2] =
+ *                       silu(gate) * up
+ *   VILA_FLAG_STATIC_W  the weight matrix is a parameter that no earlier kernel in this stream is
+ *                       still writing: the kernel may fetch it BEFORE the programmatic-dependent-launch
+ *                       wait (all vila_* kernels are launched with PDL so that prologues and weight
+ *                       prefetch overlap the predecessor's tail). Leave it clear for weights produced
+ *                       on the fly. */
+#define VILA_FLAG_SWIGLU 1
+#define VILA_FLAG_STATIC_W 2
+
 const char* vila_last_error(void);
 int vila_abi_version(void);
+/* Register caller-owned, ZERO-INITIALISED device scratch (256-byte aligned) used by vila_linear's
+ * stream-K schedule for fp32 partial sums (64 KiB of counters + M*N*4 bytes per call that uses it;
+ * calls that do not fit simply use the data-parallel schedule).  The kernels leave it zeroed again.
+ * One workspace serves one stream at a time.  ptr == NULL unregisters. */
+int vila_set_workspace(void* ptr, uint64_t bytes);
 /* fills SM count and compute capability of the current device */
 int vila_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---------------------------------------------------------------------------------------------
  * vila_linear — out[M,N] = epilogue(x[M,K] · w[N,K]^T)        (tcgen05 / TMEM / TMA GEMM)
  *   epilogue: (+bias[N]) -> act -> (+residual[row % res_row_mod or row, :])   or SwiGLU:
- *   swiglu != 0: w rows are interleaved (gate_0, up_0, gate_1, up_1, ...) and out is [M, N/2] =
- *   silu(gate) * up.
+ *   flags & VILA_FLAG_SWIGLU: w rows are interleaved (gate_0, up_0, gate_1, up_1, ...) and out is
+ *   [M, N/2] = silu(gate) * up.
  * Replaces nn.Linear (+ the ATen GELU / SiLU*mul / residual add that follows it):
  *   SigLIP q/k/v/out_proj, fc1/fc2 : llava/model/multimodal_encoder/siglip/modeling_siglip.py:384-387,707-715,752,757
  *   patch-embed Conv2d (as im2col GEMM, residual = position embedding with res_row_mod = #patches): :269-275,322-328
@@ -50,11 +66,11 @@ int vila_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * ------------------------------------------------------------------------------------------- */
 int vila_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const void* bias,
                 const void* residual, int64_t ld_res, int res_row_mod, void* out, int64_t ldo,
-                int M, int N, int K, int act, int swiglu, void* stream);
+                int M, int N, int K, int act, int flags, void* stream);
 /* test hook: same, forcing the N tile (64 / 128 / 256) */
 int vila_linear_cfg(int block_n, const void* x, int64_t ldx, const void* w, int64_t ldw,
                     const void* bias, const void* residual, int64_t ld_res, int res_row_mod,
-                    void* out, int64_t ldo, int M, int N, int K, int act, int swiglu, void* stream);
+                    void* out, int64_t ldo, int M, int N, int K, int act, int flags, void* stream);
 
 /* nn.LayerNorm over the last dim (modeling_siglip.py:723,725,746,755; base_projector.py:147) */
 int vila_layernorm(const void* x, const void* weight, const void* bias, void* out, int rows,
@@ -128,7 +144,9 @@ typedef struct vila_gemv_params {
   float norm_eps;
   const void* residual;
   void* y;
-  int32_t N, K, swiglu;
+  int32_t N, K;
+  int32_t flags; /* VILA_FLAG_SWIGLU: rows interleaved (gate, up), y is [N/2];
+                    VILA_FLAG_STATIC_W: see below */
   unsigned long long* argmax_key; /* device u64, zero before the first launch */
 } vila_gemv_params;
 int vila_gemv(const vila_gemv_params* p, void* stream);

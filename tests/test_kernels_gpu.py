@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 
 def _ops():
     from vila_b200 import ops
+    ops.ensure_workspace("cuda")
     return ops
 
 
@@ -42,7 +43,7 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("block_n", [None, 64, 128, 256])
+@pytest.mark.parametrize("block_n", [None, 64, 128, 256, 1064, 1128, 1256])  # 1000+: forced stream-K
 def test_linear_plain(cuda, M, N, K, block_n):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
@@ -72,6 +73,52 @@ def test_linear_epilogues(cuda, act, with_res):
     if with_res:
         ref = rb(ref + res.float())
     assert rel_err(out, ref) < 1e-2
+
+
+def test_linear_streamk_epilogues_and_workspace_is_clean(cuda):
+    """stream-K partial tiles go through the fp32 workspace; the epilogue (bias, GELU, residual,
+    SwiGLU) must be applied exactly once and the workspace must be left zeroed."""
+    ops = _ops()
+    ws = ops.ensure_workspace("cuda")
+    g = torch.Generator(device="cuda").manual_seed(77)
+    for (M, N, K) in [(279, 3584, 18944), (1024, 1152, 4304), (279, 1024, 2048)]:
+        x = bf(torch.randn(M, K, device=cuda, generator=g))
+        w = bf(torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K))
+        b = bf(torch.randn(N, device=cuda, generator=g))
+        res = bf(torch.randn(M, N, device=cuda, generator=g))
+        for bn in (1064, 1128, 1256):
+            out = ops.linear(x, w, b, act=1, residual=res, block_n=bn, static_w=True)
+            ref = rb(rb(O.gelu_tanh(rb(x.float() @ w.float().t() + b.float()))) + res.float())
+            assert rel_err(out, ref) < 1e-2, (M, N, K, bn)
+            out2 = ops.linear(x, w, swiglu=True, block_n=bn)
+            gate = rb(x.float() @ w.float()[0::2].t())
+            up = rb(x.float() @ w.float()[1::2].t())
+            assert rel_err(out2, rb(rb(F.silu(gate)) * up)) < 1e-2
+            torch.cuda.synchronize()
+            assert int(ws.view(torch.int32).abs().max()) == 0
+
+
+def test_linear_chain_under_pdl(cuda):
+    """Back-to-back dependent kernels (programmatic dependent launch): every consumer must wait for
+    its producer; weights flagged static may be fetched early."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(78)
+    x = bf(torch.randn(300, 1024, device=cuda, generator=g))
+    ws_ = [bf(torch.randn(1024, 1024, device=cuda, generator=g) / 32) for _ in range(6)]
+    nw = bf(torch.ones(1024, device=cuda))
+    h = x
+    ref = x.float()
+    for w in ws_:
+        h = ops.linear(ops.rmsnorm(h.clone(), nw, 1e-6), w, static_w=True)
+        ref = rb(O.rms_norm(ref.to(torch.bfloat16), nw, 1e-6).float() @ w.float().t())
+    assert rel_err(h, ref) < 3e-2
+    # in-place residual chains (out aliases residual)
+    y = x.clone()
+    r = x.float()
+    for w in ws_:
+        ops.linear(y.clone(), w, residual=y, out=y, static_w=True)
+        r = rb(rb(r @ w.float().t()) + r)
+    assert rel_err(y, r) < 3e-2
 
 
 def test_linear_posemb_residual_and_strides(cuda):

@@ -31,7 +31,7 @@ class GemvParams(C.Structure):
     _fields_ = [
         ("x", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("norm_w", c_void_p),
         ("norm_eps", c_float), ("residual", c_void_p), ("y", c_void_p),
-        ("N", C.c_int32), ("K", C.c_int32), ("swiglu", C.c_int32),
+        ("N", C.c_int32), ("K", C.c_int32), ("flags", C.c_int32),
         ("argmax_key", c_void_p),
     ]
 
@@ -50,6 +50,7 @@ class DecodeAttnParams(C.Structure):
 SIGNATURES = {
     "vila_abi_version": [],
     "vila_device_info": [C.POINTER(c_int)] * 3,
+    "vila_set_workspace": [c_void_p, C.c_uint64],
     "vila_linear": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_void_p,
                     c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "vila_linear_cfg": [c_int, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int,

@@ -41,6 +41,8 @@ extern "C" {
 const char* vila_last_error(void) { return vb::last_error(); }
 int vila_abi_version(void) { return 1; }
 
+int vila_set_workspace(void* ptr, uint64_t bytes) { return vb::set_workspace(ptr, (size_t)bytes); }
+
 int vila_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
   VB_CUDA(cudaGetDevice(&dev));
@@ -51,14 +53,15 @@ int vila_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 static vb::GemmEpilogue make_epi(const void* bias, const void* residual, int64_t ld_res,
-                                 int res_row_mod, int act, int swiglu) {
+                                 int res_row_mod, int act, int flags) {
   vb::GemmEpilogue e;
   e.bias = cb(bias);
   e.residual = cb(residual);
   e.ld_res = static_cast<int>(ld_res);
   e.res_row_mod = res_row_mod;
   e.act = act;
-  e.swiglu = swiglu;
+  e.swiglu = (flags & VILA_FLAG_SWIGLU) ? 1 : 0;
+  e.static_w = (flags & VILA_FLAG_STATIC_W) ? 1 : 0;
   return e;
 }
 
@@ -169,7 +172,7 @@ int vila_gemv(const vila_gemv_params* p, void* stream) {
   g.y = mb(p->y);
   g.N = p->N;
   g.K = p->K;
-  g.swiglu = p->swiglu;
+  g.flags = p->flags;
   g.argmax_key = p->argmax_key;
   return vb::gemv_bf16(g, st(stream));
 }

@@ -65,6 +65,20 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- programmatic dependent launch (PDL) device side ----
+// wait: all prerequisite grids have completed and their memory is visible (no-op without PDL)
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// allow the dependent grid to start launching as SM resources free up
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// asynchronous bulk prefetch of [p, p+bytes) into L2 (bytes % 16 == 0)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // streaming 128-bit global load (read once: do not allocate in L1)
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;
@@ -274,6 +288,27 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_elems, const uint32_t* box, uint32_t swizzle_bytes);
 int num_sms();
+bool pdl_enabled();  // programmatic dependent launch on unless VILA_B200_NO_PDL=1
+
+// Launch with programmatic stream serialization (PDL): the kernel may become resident while its
+// predecessor in the stream is still draining; it must execute griddep_wait() before touching
+// anything the predecessor produced (or that the predecessor still reads). Works inside CUDA-graph
+// capture (programmatic dependency edges).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 const char* last_error();
 
 }  // namespace vb

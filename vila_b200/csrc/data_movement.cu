@@ -20,6 +20,8 @@ inline int grid_for(long total_items, int threads, int items_per_thread = 1) {
 // ------------------------------------------------------------------------------------------------
 __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ pix, __nv_bfloat16* __restrict__ out,
                               int B, int C, int H, int W, int P, int k_pad) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int gh = H / P, gw = W / P;
   const int kk = C * P * P;
   // one thread handles one (row, c, ky) strip of P contiguous pixels (28 bytes for P=14)
@@ -55,6 +57,8 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ pix, __nv_bfloat
 // ------------------------------------------------------------------------------------------------
 __global__ void s2d_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int h, int w,
                            int Cv, int r) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int ho = (h + r - 1) / r, wo = (w + r - 1) / r;
   const long total = (long)B * ho * wo * r * r * Cv;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
@@ -89,6 +93,8 @@ struct S2Args {
 };
 __global__ void s2_merge_kernel(const __nv_bfloat16* __restrict__ tiles,
                                 __nv_bfloat16* __restrict__ out, S2Args a) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int Cv = a.C / 8;
   const int OH = a.out_bh * a.side, OW = a.out_bw * a.side;
   const long total = (long)OH * OW * a.n_scales * Cv;
@@ -133,6 +139,8 @@ __global__ void s2_merge_kernel(const __nv_bfloat16* __restrict__ tiles,
 // out [(bh*s) * (bw*s), C]
 __global__ void chessboard_kernel(const uint4* __restrict__ tiles, uint4* __restrict__ out, int bh,
                                   int bw, int s, int Cv) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long total = (long)bh * s * bw * s * Cv;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
        idx += (long)gridDim.x * blockDim.x) {
@@ -151,6 +159,8 @@ __global__ void chessboard_kernel(const uint4* __restrict__ tiles, uint4* __rest
 // roundings: t-pool -> bf16 -> h-pool -> bf16 -> w-pool -> bf16.
 __global__ void tsp_pool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                 int T, int h, int w, int C, int pt, int ph, int pw) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int To = T / pt, ho = h / ph, wo = w / pw;
   const long total = (long)To * ho * wo * C;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
@@ -182,6 +192,8 @@ __global__ void tsp_pool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
 __global__ void embed_splice_kernel(const uint4* __restrict__ table, const uint4* __restrict__ media,
                                     const int32_t* __restrict__ src, uint4* __restrict__ out,
                                     int rows, int Cv) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long total = (long)rows * Cv;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
        idx += (long)gridDim.x * blockDim.x) {
@@ -202,6 +214,8 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* _
                                __nv_bfloat16* __restrict__ k_pool,
                                __nv_bfloat16* __restrict__ v_pool,
                                const int32_t* __restrict__ page_table, int cache_pos0) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int half = D / 2;
   const int Ht = Hq + 2 * Hkv;
   const long total = (long)S * Ht * half;
@@ -248,8 +262,7 @@ int im2col_patch14(const __nv_bfloat16* pixels, __nv_bfloat16* out, int B, int C
   VB_CHECK(k_pad >= C * patch * patch && k_pad % 8 == 0, "im2col: bad k_pad %d", k_pad);
   const long strips = (long)B * (H / patch) * (W / patch) * C * patch;
   if (strips == 0) return 0;
-  im2col_kernel<<<grid_for(strips, 256), 256, 0, stream>>>(pixels, out, B, C, H, W, patch, k_pad);
-  VB_CUDA(cudaGetLastError());
+  VB_CUDA(launch_pdl(im2col_kernel, dim3(grid_for(strips, 256)), dim3(256), 0, stream, pixels, out, B, C, H, W, patch, k_pad));
   return 0;
 }
 
@@ -259,9 +272,8 @@ int space_to_depth(const __nv_bfloat16* x, __nv_bfloat16* out, int B, int h, int
   VB_CHECK(r == 2 || r == 3, "space_to_depth: r must be 2 or 3 (got %d)", r);
   const long total = (long)B * ((h + r - 1) / r) * ((w + r - 1) / r) * r * r * (C / 8);
   if (total == 0) return 0;
-  s2d_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
-                                                      reinterpret_cast<uint4*>(out), B, h, w, C / 8, r);
-  VB_CUDA(cudaGetLastError());
+  VB_CUDA(launch_pdl(s2d_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, reinterpret_cast<const uint4*>(x),
+                                                      reinterpret_cast<uint4*>(out), B, h, w, C / 8, r));
   return 0;
 }
 
@@ -284,8 +296,7 @@ int s2_merge(const __nv_bfloat16* tiles, __nv_bfloat16* out, int side, int C, in
     if (!share_tile) t0 += a.sh[s] * a.sw[s];
   }
   const long total = (long)out_bh * side * out_bw * side * n_scales * (C / 8);
-  s2_merge_kernel<<<grid_for(total, 256), 256, 0, stream>>>(tiles, out, a);
-  VB_CUDA(cudaGetLastError());
+  VB_CUDA(launch_pdl(s2_merge_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, tiles, out, a));
   return 0;
 }
 
@@ -294,9 +305,8 @@ int chessboard_merge(const __nv_bfloat16* tiles, __nv_bfloat16* out, int bh, int
   VB_CHECK(C % 8 == 0, "chessboard_merge: C must be a multiple of 8");
   const long total = (long)bh * s * bw * s * (C / 8);
   if (total == 0) return 0;
-  chessboard_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
-      reinterpret_cast<const uint4*>(tiles), reinterpret_cast<uint4*>(out), bh, bw, s, C / 8);
-  VB_CUDA(cudaGetLastError());
+  VB_CUDA(launch_pdl(chessboard_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, 
+      reinterpret_cast<const uint4*>(tiles), reinterpret_cast<uint4*>(out), bh, bw, s, C / 8));
   return 0;
 }
 
@@ -306,8 +316,7 @@ int tsp_pool(const __nv_bfloat16* x, __nv_bfloat16* out, int T, int h, int w, in
            "tsp_pool: pool sizes (%d,%d,%d) must divide (%d,%d,%d)", pt, ph, pw, T, h, w);
   const long total = (long)(T / pt) * (h / ph) * (w / pw) * C;
   if (total == 0) return 0;
-  tsp_pool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, out, T, h, w, C, pt, ph, pw);
-  VB_CUDA(cudaGetLastError());
+  VB_CUDA(launch_pdl(tsp_pool_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, x, out, T, h, w, C, pt, ph, pw));
   return 0;
 }
 
@@ -316,10 +325,9 @@ int embed_splice(const __nv_bfloat16* table, const __nv_bfloat16* media, const i
   VB_CHECK(cols % 8 == 0, "embed_splice: cols must be a multiple of 8");
   if (rows == 0) return 0;
   const long total = (long)rows * (cols / 8);
-  embed_splice_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+  VB_CUDA(launch_pdl(embed_splice_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, 
       reinterpret_cast<const uint4*>(table), reinterpret_cast<const uint4*>(media), src,
-      reinterpret_cast<uint4*>(out), rows, cols / 8);
-  VB_CUDA(cudaGetLastError());
+      reinterpret_cast<uint4*>(out), rows, cols / 8));
   return 0;
 }
 
@@ -330,9 +338,8 @@ int rope_kv_append(__nv_bfloat16* qkv, const int32_t* positions, int S, int Hq, 
   VB_CHECK(k_pool == nullptr || page_table != nullptr, "rope_kv_append: page_table required");
   if (S == 0) return 0;
   const long total = (long)S * (Hq + 2 * Hkv) * (D / 2);
-  rope_kv_kernel<<<grid_for(total, 256), 256, 0, stream>>>(qkv, positions, S, Hq, Hkv, D, inv_freq,
-                                                          k_pool, v_pool, page_table, cache_pos0);
-  VB_CUDA(cudaGetLastError());
+  VB_CUDA(launch_pdl(rope_kv_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, qkv, positions, S, Hq, Hkv, D, inv_freq,
+                                                          k_pool, v_pool, page_table, cache_pos0));
   return 0;
 }
 

@@ -18,6 +18,7 @@ namespace {
 
 constexpr int kGemvThreads = 512;
 constexpr int kGemvWarps = kGemvThreads / 32;
+constexpr size_t kGemvPrefetchBytes = 256 * 1024;  // per-CTA L2 prefetch before the PDL wait
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
@@ -53,6 +54,21 @@ gemv_kernel(GemvParams p, int rows_per_block, int ksplit) {
   const int nrows = min(rows_per_block, p.N - row0);
   if (nrows <= 0) return;
   const int nvec = p.K >> 3;
+
+  // ---- PDL prologue: let the next kernel become resident, and pull the head of this CTA's
+  // (static) weight slab into L2 while the predecessor kernel is still draining ----
+  griddep_launch_dependents();
+  if (p.flags & 2) {
+    const char* slab = reinterpret_cast<const char*>(p.w + static_cast<size_t>(row0) * p.K);
+    const size_t slab_bytes = static_cast<size_t>(nrows) * p.K * 2;
+    const size_t cap = slab_bytes < kGemvPrefetchBytes ? slab_bytes : kGemvPrefetchBytes;
+    for (size_t off = static_cast<size_t>(threadIdx.x) * 2048; off < cap;
+         off += static_cast<size_t>(kGemvThreads) * 2048) {
+      const size_t n = cap - off < 2048 ? cap - off : 2048;
+      prefetch_l2_bulk(slab + off, static_cast<uint32_t>(n & ~static_cast<size_t>(15)));
+    }
+  }
+  griddep_wait();
 
   // ---- prologue: stage x (optionally RMS-normalised) in shared memory ----
   const uint4* xg = reinterpret_cast<const uint4*>(p.x);
@@ -94,37 +110,52 @@ gemv_kernel(GemvParams p, int rows_per_block, int ksplit) {
   if (threadIdx.x == 0) best_s = 0ull;
   __syncthreads();
 
-  // ---- main loop: (row, k-part) items, one warp per item, 512 B of a row per warp-load ----
-  const int nchunks = (nvec + 31) >> 5;  // 32 vectors (256 elements) per chunk
+  // ---- main loop: this warp's (row, k-part) items form ONE flat stream of 512-byte row chunks;
+  // UNROLL independent 128-bit loads per lane stay in flight across item boundaries ----
+  const int nchunks = (nvec + 31) >> 5;           // 32 vectors (256 elements) per chunk
+  const int cpi = (nchunks + ksplit - 1) / ksplit;  // chunks per item
   const int items = nrows * ksplit;
-  for (int item = warp; item < items; item += kGemvWarps) {
-    const int r = item / ksplit, part = item - r * ksplit;
-    const int c0 = (part * nchunks) / ksplit, c1 = ((part + 1) * nchunks) / ksplit;
-    const uint4* wrow = reinterpret_cast<const uint4*>(p.w + static_cast<size_t>(row0 + r) * p.K);
-    float sum = 0.f;
-    for (int c = c0; c < c1; c += UNROLL) {
-      uint4 wv[UNROLL];
+  const int my_items = items > warp ? (items - warp + kGemvWarps - 1) / kGemvWarps : 0;
+  const int total = my_items * cpi;
+  float sum = 0.f;
+  for (int f0 = 0; f0 < total; f0 += UNROLL) {
+    uint4 wv[UNROLL];
+    int vidx[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int vi = (c + u) * 32 + lane;
-        wv[u] = (c + u < c1 && vi < nvec) ? ldg_stream(wrow + vi) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int vi = (c + u) * 32 + lane;
-        if (c + u < c1 && vi < nvec) sum = dot8(wv[u], xs[vi], sum);
-      }
+    for (int u = 0; u < UNROLL; ++u) {
+      const int f = f0 + u;
+      const int it = f / cpi, ch = f - it * cpi;
+      const int item = warp + it * kGemvWarps;
+      const int r = item / ksplit, part = item - r * ksplit;
+      const int vi = (part * cpi + ch) * 32 + lane;
+      const bool ok = f < total && vi < nvec;
+      vidx[u] = ok ? vi : -1;
+      wv[u] = ok ? ldg_stream(reinterpret_cast<const uint4*>(p.w + static_cast<size_t>(row0 + r) * p.K) + vi)
+                 : make_uint4(0, 0, 0, 0);
     }
-    sum = warp_sum(sum);
-    if (lane == 0) {
-      if (ksplit == 1) acc[r] = sum;
-      else atomicAdd(&acc[r], sum);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int f = f0 + u;
+      if (f < total) {  // warp-uniform
+        if (vidx[u] >= 0) sum = dot8(wv[u], xs[vidx[u]], sum);
+        const int it = f / cpi, ch = f - it * cpi;
+        if (ch == cpi - 1) {  // item finished: reduce and publish
+          const float tot = warp_sum(sum);
+          sum = 0.f;
+          if (lane == 0) {
+            const int item = warp + it * kGemvWarps;
+            const int r = item / ksplit;
+            if (ksplit == 1) acc[r] = tot;
+            else atomicAdd(&acc[r], tot);
+          }
+        }
+      }
     }
   }
   __syncthreads();
 
   // ---- epilogue ----
-  if (p.swiglu) {
+  if (p.flags & 1) {
     for (int j = threadIdx.x; j < (nrows >> 1); j += blockDim.x) {
       float g = acc[2 * j], u = acc[2 * j + 1];
       if (p.bias) {
@@ -169,6 +200,8 @@ __global__ void argmax_finalize_kernel(unsigned long long* key, int32_t* token_o
                                        int32_t* position, const uint4* __restrict__ embed_table,
                                        uint4* __restrict__ x_next, int hidden_vec) {
   __shared__ int32_t tok_s;
+  griddep_launch_dependents();
+  griddep_wait();
   if (threadIdx.x == 0) {
     const unsigned long long k = *key;
     const int32_t tok = static_cast<int32_t>(0xffffffffu - static_cast<uint32_t>(k & 0xffffffffull));
@@ -207,6 +240,8 @@ decode_attn_kernel(DecodeAttnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / LPT;        // which of the 2 tokens this half-warp handles
   const int dl = lane % LPT;         // d-slice index
+  griddep_launch_dependents();
+  griddep_wait();
   const int pos = *p.position;       // index of the new token == number of cached tokens
   const int n_tok = pos + 1;
 
@@ -378,10 +413,10 @@ decode_attn_kernel(DecodeAttnParams p) {
 
 int gemv_bf16(const GemvParams& p, cudaStream_t stream) {
   VB_CHECK(p.N > 0 && p.K > 0 && p.K % 8 == 0, "gemv: bad shape N=%d K=%d (K %% 8 == 0)", p.N, p.K);
-  VB_CHECK(!p.swiglu || p.N % 2 == 0, "gemv: swiglu needs even N");
+  VB_CHECK(!(p.flags & 1) || p.N % 2 == 0, "gemv: swiglu needs even N");
   const int sms = num_sms();
   int rows_per_block = (p.N + sms - 1) / sms;
-  if (p.swiglu && (rows_per_block & 1)) rows_per_block += 1;
+  if ((p.flags & 1) && (rows_per_block & 1)) rows_per_block += 1;
   const int grid = (p.N + rows_per_block - 1) / rows_per_block;
   const int nchunks = ((p.K >> 3) + 31) >> 5;
   int ksplit = 1;
@@ -395,8 +430,7 @@ int gemv_bf16(const GemvParams& p, cudaStream_t stream) {
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  kern<<<grid, kGemvThreads, smem, stream>>>(p, rows_per_block, ksplit);
-  VB_CUDA(cudaGetLastError());
+  VB_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemvThreads), smem, stream, p, rows_per_block, ksplit));
   return 0;
 }
 
@@ -404,10 +438,9 @@ int argmax_finalize(unsigned long long* key, int32_t* token_out, int32_t* token_
                        int32_t* step_counter, int32_t* position, const __nv_bfloat16* embed_table,
                        __nv_bfloat16* x_next, int hidden, cudaStream_t stream) {
   VB_CHECK(hidden % 8 == 0, "argmax_finalize: hidden must be a multiple of 8");
-  argmax_finalize_kernel<<<1, 256, 0, stream>>>(key, token_out, token_hist, step_counter, position,
-                                               reinterpret_cast<const uint4*>(embed_table),
-                                               reinterpret_cast<uint4*>(x_next), hidden / 8);
-  VB_CUDA(cudaGetLastError());
+  VB_CUDA(launch_pdl(argmax_finalize_kernel, dim3(1), dim3(256), 0, stream, key, token_out, token_hist,
+                     step_counter, position, reinterpret_cast<const uint4*>(embed_table),
+                     reinterpret_cast<uint4*>(x_next), hidden / 8));
   return 0;
 }
 
@@ -422,8 +455,12 @@ int decode_attention(const DecodeAttnParams& p, cudaStream_t stream) {
   case GG: {                                                                                    \
     auto kern = decode_attn_kernel<128, GG>;                                                    \
     const size_t smem = (size_t)kDaWarps * 2 * GG * (128 + 2) * sizeof(float);                  \
-    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, kDaThreads, smem, stream>>>(p);                                                \
+    static bool attr_done = false;                                                              \
+    if (!attr_done) {                                                                           \
+      VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_done = true;                                                                         \
+    }                                                                                           \
+    VB_CUDA(launch_pdl(kern, grid, dim3(kDaThreads), smem, stream, p));                         \
     break;                                                                                      \
   }
   switch (G) {
@@ -437,7 +474,6 @@ int decode_attention(const DecodeAttnParams& p, cudaStream_t stream) {
       return 1;
   }
 #undef VB_DA_CASE
-  VB_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -118,6 +118,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_launch_dependents();
+  griddep_wait();  // Q/K/V come from the predecessor; O may alias memory it still reads
 
   if (warp == 4) {
     // ===================== TMA producer =====================
@@ -364,8 +366,7 @@ int launch_fmha(const FmhaParams& p, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((p.Sq + BQ - 1) / BQ, p.Hq, p.B);
-  kern<<<grid, kThreads, C::kSmem, stream>>>(tq, tk, tv, a);
-  VB_CUDA(cudaGetLastError());
+  VB_CUDA(launch_pdl(kern, grid, dim3(kThreads), C::kSmem, stream, tq, tk, tv, a));
   return 0;
 }
 

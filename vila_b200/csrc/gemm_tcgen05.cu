@@ -2,10 +2,16 @@
 //
 //   * operands staged global -> shared by TMA (cp.async.bulk.tensor, 128B swizzle, K-major)
 //   * tcgen05.mma (cta_group::1, kind::f16, 128 x BLOCK_N x 16) issued by ONE thread
-//   * fp32 accumulators live in TMEM, double-buffered so the epilogue of tile i overlaps the
-//     main loop of tile i+1
+//   * fp32 accumulators live in TMEM, double-buffered so the epilogue of one work segment overlaps
+//     the main loop of the next
 //   * epilogue warps read TMEM with tcgen05.ld (lane == output row) and fuse
 //     bias / GELU / SwiGLU / residual (+ broadcast "row modulo" residual for position embeddings)
+//   * scheduling: data-parallel over output tiles, or STREAM-K when the tile count does not fill the
+//     148 SMs evenly (skinny prefill GEMMs, M = 280): the (tile, k-block) iteration space is cut
+//     into equal contiguous ranges, partial tiles are reduced with red.global.add.v4.f32 into an
+//     fp32 workspace and the last-arriving CTA applies the epilogue (self-cleaning workspace)
+//   * programmatic dependent launch: barrier init / TMEM alloc / descriptor prefetch and — for
+//     parameter matrices — the first pipeline stages of W overlap the predecessor kernel's tail
 //
 // Replaces the cuBLAS calls behind nn.Linear on the reference hot path:
 //   SigLIP q/k/v/out_proj, fc1/fc2      (modeling_siglip.py:384-387,707-715)
@@ -45,6 +51,57 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ float4 ld_cg_v4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// Work decomposition shared by the three warp roles: a CTA walks a sequence of segments
+// (tile, [kb0, kb1)).  Data-parallel: whole tiles blockIdx.x, +gridDim.x, ...  Stream-K: the
+// contiguous iteration range [it0, it1) of the (tile, k-block) space.
+struct Sched {
+  int nkb, num_m_blocks, num_tiles;
+  int stream_k;
+  long it, it_end;  // stream-K
+  int tile;         // data-parallel
+  __device__ __forceinline__ Sched(int M, int N, int K, int block_n, int stream_k_) {
+    nkb = (K + BLOCK_K - 1) / BLOCK_K;
+    num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+    num_tiles = num_m_blocks * ((N + block_n - 1) / block_n);
+    stream_k = stream_k_;
+    const long total = static_cast<long>(num_tiles) * nkb;
+    it = total * blockIdx.x / gridDim.x;
+    it_end = total * (blockIdx.x + 1) / gridDim.x;
+    tile = blockIdx.x;
+  }
+  // returns false when done; otherwise the next segment
+  __device__ __forceinline__ bool next(int& t, int& kb0, int& kb1) {
+    if (stream_k) {
+      if (it >= it_end) return false;
+      t = static_cast<int>(it / nkb);
+      kb0 = static_cast<int>(it - static_cast<long>(t) * nkb);
+      const long rem = it_end - it;
+      kb1 = (nkb - kb0) < rem ? nkb : kb0 + static_cast<int>(rem);
+      it += kb1 - kb0;
+      return true;
+    }
+    if (tile >= num_tiles) return false;
+    t = tile;
+    kb0 = 0;
+    kb1 = nkb;
+    tile += gridDim.x;
+    return true;
+  }
+};
+
 template <int BLOCK_N, int kStages>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -61,14 +118,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint32_t* last_flag = tmem_ptr + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
   const int num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
-  const int num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = num_m_blocks * num_n_blocks;
-  const int num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  const int stream_k = epi.split_k > 1 ? 1 : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -91,42 +146,73 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      Sched sch(M, N, K, BLOCK_N, stream_k);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m_blocks;
-        const int n_blk = tile / num_m_blocks;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-          tma_load_2d(smem_a + stage * S::kABytes, &tmap_a, &full_bar[stage], kb * BLOCK_K,
-                      m_blk * BLOCK_M);
-          tma_load_2d(smem_b + stage * S::kBBytes, &tmap_w, &full_bar[stage], kb * BLOCK_K,
+      int t, kb0, kb1;
+      bool waited = false;
+      // W is a parameter: fetch its first stages before the dependency wait (A comes after)
+      int pre = 0;
+      int pt = 0, pkb0 = 0, pkb1 = 0;
+      Sched peek = sch;
+      const bool have_first = peek.next(pt, pkb0, pkb1);
+      if (epi.static_w && have_first) {
+        pre = min(kStages, pkb1 - pkb0);
+        const int n_blk = pt / num_m_blocks;
+        for (int i = 0; i < pre; ++i) {
+          mbar_arrive_expect_tx(&full_bar[i], S::kStageBytes);
+          tma_load_2d(smem_b + i * S::kBBytes, &tmap_w, &full_bar[i], (pkb0 + i) * BLOCK_K,
                       n_blk * BLOCK_N);
+        }
+      }
+      griddep_wait();
+      waited = true;
+      (void)waited;
+      bool first = true;
+      while (sch.next(t, kb0, kb1)) {
+        const int m_blk = t % num_m_blocks;
+        const int n_blk = t / num_m_blocks;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (first && (kb - kb0) < pre) {
+            // W already in flight for this stage: only A is missing
+            tma_load_2d(smem_a + stage * S::kABytes, &tmap_a, &full_bar[stage], kb * BLOCK_K,
+                        m_blk * BLOCK_M);
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+            tma_load_2d(smem_a + stage * S::kABytes, &tmap_a, &full_bar[stage], kb * BLOCK_K,
+                        m_blk * BLOCK_M);
+            tma_load_2d(smem_b + stage * S::kBBytes, &tmap_w, &full_bar[stage], kb * BLOCK_K,
+                        n_blk * BLOCK_N);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
+        first = false;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+      Sched sch(M, N, K, BLOCK_N, stream_k);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int t, kb0, kb1;
+      while (sch.next(t, kb0, kb1)) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t a_desc =
@@ -136,7 +222,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) along K inside the 128B swizzle atom: +2 in addr>>4 units
-            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                     (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
           if (++stage == kStages) {
@@ -154,102 +241,166 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else {
     // ===================== epilogue warps (TMEM -> regs -> global) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int epi_tid = threadIdx.x - 64;
+    Sched sch(M, N, K, BLOCK_N, stream_k);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % num_m_blocks;
-      const int n_blk = tile / num_m_blocks;
+    int t, kb0, kb1;
+    griddep_wait();  // C / residual / workspace may still be in use by the predecessor
+    while (sch.next(t, kb0, kb1)) {
+      const int m_blk = t % num_m_blocks;
+      const int n_blk = t / num_m_blocks;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int row = m_blk * BLOCK_M + quad * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N;
-      const __nv_bfloat16* res_row = nullptr;
-      if (epi.residual != nullptr && row_ok) {
-        const int rr = epi.res_row_mod > 0 ? (row % epi.res_row_mod) : row;
-        res_row = epi.residual + static_cast<size_t>(rr) * epi.ld_res;
-      }
+      const bool partial = (kb0 != 0) || (kb1 != sch.nkb);
+      bool finalize = true;       // apply the epilogue and write C
+      bool from_ws = false;       // accumulator comes from the fp32 workspace
+      if (partial) {
+        // ---- stream-K partial tile: reduce into the fp32 workspace ----
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, r);
-        tmem_ld_wait();
-        const int n0 = n_blk * BLOCK_N + c * 32;
-        if (n0 >= N) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (epi.bias != nullptr) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (n0 + g * 8 < N) {
-              const uint4 b = ldg_v4(epi.bias + n0 + g * 8);
-              v[g * 8 + 0] += bf_lo(b.x);
-              v[g * 8 + 1] += bf_hi(b.x);
-              v[g * 8 + 2] += bf_lo(b.y);
-              v[g * 8 + 3] += bf_hi(b.y);
-              v[g * 8 + 4] += bf_lo(b.z);
-              v[g * 8 + 5] += bf_hi(b.z);
-              v[g * 8 + 6] += bf_lo(b.w);
-              v[g * 8 + 7] += bf_hi(b.w);
-            }
-          }
-        }
-        if (epi.swiglu) {
-          // interleaved (gate, up) column pairs -> 16 outputs: silu(gate) * up,
-          // rounding to bf16 at the points the reference's unfused ops do.
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          const int n0 = n_blk * BLOCK_N + c * 32;
           if (row_ok) {
-            uint32_t o[8];
+            float* wsp = epi.splitk_ws + static_cast<size_t>(row) * N + n0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float g0 = bf16_round(v[4 * j + 0]), u0 = bf16_round(v[4 * j + 1]);
-              float g1 = bf16_round(v[4 * j + 2]), u1 = bf16_round(v[4 * j + 3]);
-              float a0 = bf16_round(silu_f(g0)) * u0;
-              float a1 = bf16_round(silu_f(g1)) * u1;
-              o[j] = pack_bf16(a0, a1);
+            for (int g = 0; g < 8; ++g) {
+              if (n0 + g * 4 < N)
+                red_add_v4(wsp + g * 4, __uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                           __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
             }
-            __nv_bfloat16* dst = C + static_cast<size_t>(row) * ldc + (n0 >> 1);
-            if (n0 + 16 <= N) stg_v4(dst, make_uint4(o[0], o[1], o[2], o[3]));
-            if (n0 + 32 <= N) stg_v4(dst + 8, make_uint4(o[4], o[5], o[6], o[7]));
-          }
-          continue;
-        }
-        if (epi.act != ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = bf16_round(v[j]);
-            v[j] = epi.act == ACT_GELU_TANH ? gelu_tanh_f(x)
-                                            : (epi.act == ACT_GELU_ERF ? gelu_erf_f(x) : silu_f(x));
           }
         }
-        if (row_ok) {
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[as]);  // TMEM stage is free again
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (epi_tid == 0) {
+          const int add = kb1 - kb0;
+          const int prev = atomicAdd(&epi.splitk_counters[t], add);
+          const int last = (prev + add == sch.nkb) ? 1 : 0;
+          if (last) epi.splitk_counters[t] = 0;  // self-cleaning
+          *last_flag = last;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        finalize = (*last_flag != 0);
+        from_ws = true;
+        if (finalize) __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone has read last_flag
+      }
+      if (finalize) {
+        const __nv_bfloat16* res_row = nullptr;
+        if (epi.residual != nullptr && row_ok) {
+          const int rr = epi.res_row_mod > 0 ? (row % epi.res_row_mod) : row;
+          res_row = epi.residual + static_cast<size_t>(rr) * epi.ld_res;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          float v[32];
+          const int n0 = n_blk * BLOCK_N + c * 32;
+          if (!from_ws) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (n0 + g * 8 < N) {
-              float* w = v + g * 8;
-              if (res_row != nullptr) {
-                const uint4 b = ldg_v4(res_row + n0 + g * 8);
-                w[0] = bf16_round(w[0]) + bf_lo(b.x);
-                w[1] = bf16_round(w[1]) + bf_hi(b.x);
-                w[2] = bf16_round(w[2]) + bf_lo(b.y);
-                w[3] = bf16_round(w[3]) + bf_hi(b.y);
-                w[4] = bf16_round(w[4]) + bf_lo(b.z);
-                w[5] = bf16_round(w[5]) + bf_hi(b.z);
-                w[6] = bf16_round(w[6]) + bf_lo(b.w);
-                w[7] = bf16_round(w[7]) + bf_hi(b.w);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          } else {
+            if (n0 >= N) continue;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            if (row_ok) {
+              float* wsp = epi.splitk_ws + static_cast<size_t>(row) * N + n0;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (n0 + g * 4 < N) {
+                  const float4 q = ld_cg_v4(wsp + g * 4);
+                  v[g * 4 + 0] = q.x; v[g * 4 + 1] = q.y; v[g * 4 + 2] = q.z; v[g * 4 + 3] = q.w;
+                  *reinterpret_cast<float4*>(wsp + g * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
               }
-              uint4 o;
-              o.x = pack_bf16(w[0], w[1]);
-              o.y = pack_bf16(w[2], w[3]);
-              o.z = pack_bf16(w[4], w[5]);
-              o.w = pack_bf16(w[6], w[7]);
-              stg_v4(C + static_cast<size_t>(row) * ldc + n0 + g * 8, o);
+            }
+          }
+          if (n0 >= N) continue;
+          if (epi.bias != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (n0 + g * 8 < N) {
+                const uint4 b = ldg_v4(epi.bias + n0 + g * 8);
+                v[g * 8 + 0] += bf_lo(b.x);
+                v[g * 8 + 1] += bf_hi(b.x);
+                v[g * 8 + 2] += bf_lo(b.y);
+                v[g * 8 + 3] += bf_hi(b.y);
+                v[g * 8 + 4] += bf_lo(b.z);
+                v[g * 8 + 5] += bf_hi(b.z);
+                v[g * 8 + 6] += bf_lo(b.w);
+                v[g * 8 + 7] += bf_hi(b.w);
+              }
+            }
+          }
+          if (epi.swiglu) {
+            // interleaved (gate, up) column pairs -> 16 outputs: silu(gate) * up,
+            // rounding to bf16 at the points the reference's unfused ops do.
+            if (row_ok) {
+              uint32_t o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float g0 = bf16_round(v[4 * j + 0]), u0 = bf16_round(v[4 * j + 1]);
+                float g1 = bf16_round(v[4 * j + 2]), u1 = bf16_round(v[4 * j + 3]);
+                float a0 = bf16_round(silu_f(g0)) * u0;
+                float a1 = bf16_round(silu_f(g1)) * u1;
+                o[j] = pack_bf16(a0, a1);
+              }
+              __nv_bfloat16* dst = C + static_cast<size_t>(row) * ldc + (n0 >> 1);
+              if (n0 + 16 <= N) stg_v4(dst, make_uint4(o[0], o[1], o[2], o[3]));
+              if (n0 + 32 <= N) stg_v4(dst + 8, make_uint4(o[4], o[5], o[6], o[7]));
+            }
+            continue;
+          }
+          if (epi.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = bf16_round(v[j]);
+              v[j] = epi.act == ACT_GELU_TANH
+                         ? gelu_tanh_f(x)
+                         : (epi.act == ACT_GELU_ERF ? gelu_erf_f(x) : silu_f(x));
+            }
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (n0 + g * 8 < N) {
+                float* w = v + g * 8;
+                if (res_row != nullptr) {
+                  const uint4 b = ldg_v4(res_row + n0 + g * 8);
+                  w[0] = bf16_round(w[0]) + bf_lo(b.x);
+                  w[1] = bf16_round(w[1]) + bf_hi(b.x);
+                  w[2] = bf16_round(w[2]) + bf_lo(b.y);
+                  w[3] = bf16_round(w[3]) + bf_hi(b.y);
+                  w[4] = bf16_round(w[4]) + bf_lo(b.z);
+                  w[5] = bf16_round(w[5]) + bf_hi(b.z);
+                  w[6] = bf16_round(w[6]) + bf_lo(b.w);
+                  w[7] = bf16_round(w[7]) + bf_hi(b.w);
+                }
+                uint4 o;
+                o.x = pack_bf16(w[0], w[1]);
+                o.y = pack_bf16(w[2], w[3]);
+                o.z = pack_bf16(w[4], w[5]);
+                o.w = pack_bf16(w[6], w[7]);
+                stg_v4(C + static_cast<size_t>(row) * ldc + n0 + g * 8, o);
+              }
             }
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[as]);
+      if (!partial) {
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[as]);
+      }
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -265,9 +416,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
+// caller-registered scratch for stream-K partial sums (vila_set_workspace)
+struct Workspace {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+Workspace g_ws;
+constexpr size_t kCounterBytes = 64 * 1024;  // 16384 tile counters
+
 template <int BLOCK_N, int kStages>
 int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
-                int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
+                int ldc, int M, int N, int K, GemmEpilogue epi, int force_stream_k,
+                cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N, kStages>;
   CUtensorMap ta, tw;
   if (make_tmap_2d_bf16(&ta, A, M, K, lda, BLOCK_M, BLOCK_K, 128)) return 1;
@@ -278,17 +438,41 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
+  const int sms = num_sms();
   const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kNumThreads, S::kTotal, stream>>>(ta, tw, C, ldc, M, N, K, epi);
-  VB_CUDA(cudaGetLastError());
+  const int nkb = (K + BLOCK_K - 1) / BLOCK_K;
+  // stream-K when whole tiles would leave SMs idle or produce a ragged last wave
+  bool sk = false;
+  const size_t need = kCounterBytes + static_cast<size_t>(M) * N * 4;
+  const bool ws_ok = g_ws.ptr != nullptr && g_ws.bytes >= need && tiles <= 16384 && N % 4 == 0;
+  if (force_stream_k >= 0) {
+    sk = force_stream_k != 0;
+  } else if (ws_ok && nkb >= 4 && tiles % sms != 0 && tiles < 4 * sms) {
+    const int waves = (tiles + sms - 1) / sms;
+    const double eff = static_cast<double>(tiles) / (static_cast<double>(waves) * sms);
+    sk = eff < 0.9;
+  }
+  if (sk && !ws_ok) {
+    set_last_error("gemm: stream-K needs a registered workspace of >= %zu bytes (vila_set_workspace)",
+                   need);
+    return 1;
+  }
+  int grid = tiles < sms ? tiles : sms;
+  epi.split_k = 1;
+  if (sk) {
+    const long total = static_cast<long>(tiles) * nkb;
+    grid = total < sms ? static_cast<int>(total) : sms;
+    epi.split_k = 2;  // any value > 1 selects the stream-K schedule
+    epi.splitk_counters = static_cast<int*>(g_ws.ptr);
+    epi.splitk_ws = reinterpret_cast<float*>(static_cast<char*>(g_ws.ptr) + kCounterBytes);
+  }
+  VB_CUDA(launch_pdl(kern, dim3(grid), dim3(kNumThreads), S::kTotal, stream, ta, tw, C, ldc, M, N,
+                     K, epi));
   return 0;
 }
 
-}  // namespace
-
-int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
-              int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
+int check_args(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
+               int ldc, int M, int N, int K, const GemmEpilogue& epi) {
   VB_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   VB_CHECK(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0,
            "gemm: K, lda, ldw must be multiples of 8 (TMA 16-byte strides): K=%d lda=%d ldw=%d", K,
@@ -299,26 +483,50 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
                (reinterpret_cast<uintptr_t>(C) & 15) == 0,
            "gemm: pointers must be 16-byte aligned");
   if (epi.swiglu) VB_CHECK(N % 32 == 0, "gemm: swiglu epilogue needs N %% 32 == 0 (N=%d)", N);
-  // Tile-shape heuristic: keep >= ~1 wave of CTAs; wide tiles when the problem is large.
+  return 0;
+}
+
+}  // namespace
+
+int set_workspace(void* ptr, size_t bytes) {
+  VB_CHECK(ptr == nullptr || bytes >= kCounterBytes + 1024, "workspace too small (%zu bytes)", bytes);
+  VB_CHECK((reinterpret_cast<uintptr_t>(ptr) & 255) == 0, "workspace must be 256-byte aligned");
+  g_ws.ptr = ptr;
+  g_ws.bytes = ptr ? bytes : 0;
+  return 0;
+}
+
+int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
+              int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
+  if (check_args(A, lda, W, ldw, C, ldc, M, N, K, epi)) return 1;
+  // Tile-shape heuristic. N=256 tiles keep the MMA (not shared-memory bandwidth) the limiter when
+  // there is enough work; N=128 otherwise; stream-K (inside launch_gemm) fixes SM under-fill.
   const int sms = num_sms();
   const int mb = (M + BLOCK_M - 1) / BLOCK_M;
   const long tiles256 = static_cast<long>(mb) * ((N + 255) / 256);
-  const long tiles128 = static_cast<long>(mb) * ((N + 127) / 128);
   if (tiles256 >= 2L * sms && N % 256 == 0)
-    return launch_gemm<256, 4>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
-  if (tiles128 >= sms / 2 || N < 128)
-    return launch_gemm<128, 6>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
-  return launch_gemm<64, 8>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
+    return launch_gemm<256, 4>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
+  if (N < 128) return launch_gemm<64, 8>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
+  return launch_gemm<128, 6>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
 }
 
-// test hook: force a tile configuration
+// test hook: force a tile configuration (block_n in {64,128,256}; +1000 forces stream-K, +2000 off)
 int gemm_bf16_cfg(int block_n, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw,
                   __nv_bfloat16* C, int ldc, int M, int N, int K, const GemmEpilogue& epi,
                   cudaStream_t stream) {
+  if (check_args(A, lda, W, ldw, C, ldc, M, N, K, epi)) return 1;
+  int fsk = -1;
+  if (block_n >= 2000) {
+    fsk = 0;
+    block_n -= 2000;
+  } else if (block_n >= 1000) {
+    fsk = 1;
+    block_n -= 1000;
+  }
   switch (block_n) {
-    case 64: return launch_gemm<64, 8>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
-    case 128: return launch_gemm<128, 6>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
-    case 256: return launch_gemm<256, 4>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
+    case 64: return launch_gemm<64, 8>(A, lda, W, ldw, C, ldc, M, N, K, epi, fsk, stream);
+    case 128: return launch_gemm<128, 6>(A, lda, W, ldw, C, ldc, M, N, K, epi, fsk, stream);
+    case 256: return launch_gemm<256, 4>(A, lda, W, ldw, C, ldc, M, N, K, epi, fsk, stream);
     default: set_last_error("gemm_bf16_cfg: unsupported block_n %d", block_n); return 1;
   }
 }

@@ -1,6 +1,7 @@
 // Host-side support: error string, SM count, TMA descriptor encoding via the driver entry point.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -17,6 +18,15 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_last_error; }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VILA_B200_NO_PDL");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int num_sms() {
   static int cached[64] = {0};

@@ -16,8 +16,15 @@ struct GemmEpilogue {
   int res_row_mod = 0;
   int act = ACT_NONE;
   int swiglu = 0;  // interleaved (gate, up) columns -> N/2 outputs of silu(gate) * up
+  int static_w = 0;  // W is a parameter: its first pipeline stages may be fetched before the PDL wait
+  // split-K (set by the launcher): fp32 partial-sum workspace [M, N] (zeroed, self-cleaning) and
+  // per-tile arrival counters (zeroed, self-cleaning)
+  float* splitk_ws = nullptr;
+  int* splitk_counters = nullptr;
+  int split_k = 1;
 };
 
+int set_workspace(void* ptr, size_t bytes);
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
               int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream);
 int gemm_bf16_cfg(int block_n, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw,
@@ -91,7 +98,7 @@ struct GemvParams {
   const __nv_bfloat16* residual;  // [N] or null (added after bias)
   __nv_bfloat16* y;               // [N] (or [N/2] with swiglu)
   int N, K;
-  int swiglu;  // rows interleaved (gate, up)
+  int flags;   // bit0: SwiGLU (rows interleaved gate, up); bit1: weights are static (L2 prefetch before PDL wait)
   // optional fused greedy argmax over y (lm_head): 64-bit packed (value, ~index) max-reduction
   unsigned long long* argmax_key;
 };

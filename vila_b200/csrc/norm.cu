@@ -28,6 +28,8 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
                  float eps) {
   extern __shared__ uint4 row_s[];  // cols/8 vectors
   __shared__ float red[32];
+  griddep_launch_dependents();
+  griddep_wait();
   const int row = blockIdx.x;
   const int nvec = cols >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * cols);
@@ -84,6 +86,8 @@ rmsnorm_kernel(__nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ 
                float eps) {
   extern __shared__ uint4 row_s[];
   __shared__ float red[32];
+  griddep_launch_dependents();
+  griddep_wait();
   const int row = blockIdx.x;
   const int nvec = cols >> 3;
   uint4* xr = reinterpret_cast<uint4*>(x + static_cast<size_t>(row) * cols);
@@ -139,8 +143,7 @@ int layernorm_bf16(const __nv_bfloat16* x, const __nv_bfloat16* w, const __nv_bf
                                  96 * 1024));
     attr = true;
   }
-  layernorm_kernel<<<rows, kNormThreads, smem, stream>>>(x, w, b, out, cols, eps);
-  VB_CUDA(cudaGetLastError());
+  VB_CUDA(launch_pdl(layernorm_kernel, dim3(rows), dim3(kNormThreads), smem, stream, x, w, b, out, cols, eps));
   return 0;
 }
 
@@ -157,8 +160,8 @@ int rmsnorm_bf16(__nv_bfloat16* x_inout, const __nv_bfloat16* residual_add,
                                  96 * 1024));
     attr = true;
   }
-  rmsnorm_kernel<<<rows, kNormThreads, smem, stream>>>(x_inout, residual_add, w, out, cols, eps);
-  VB_CUDA(cudaGetLastError());
+  VB_CUDA(launch_pdl(rmsnorm_kernel, dim3(rows), dim3(kNormThreads), smem, stream, x_inout, residual_add, w,
+                     out, cols, eps));
   return 0;
 }
 

@@ -183,6 +183,7 @@ class LlavaLlamaModel(nn.Module):
                                "has no CPU / eager fallback")
         from .. import _lib
         _lib.load()  # fail loudly if the extension is not built
+        ops.ensure_workspace(device)  # stream-K scratch for the skinny prefill / ViT GEMMs
         self.config = config
         dtype = torch.bfloat16
         self.llm = Qwen2ForCausalLM(config.llm_cfg, device, dtype)

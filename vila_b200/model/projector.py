@@ -82,7 +82,7 @@ class MultimodalProjector(nn.Module):
             if op == "ln":
                 h = ops.layernorm(h, mod.weight, mod.bias, self.LN_EPS)
             elif op == "lin_gelu":
-                h = ops.linear(h, mod.weight, mod.bias, act=ops.ACT_GELU_ERF)
+                h = ops.linear(h, mod.weight, mod.bias, act=ops.ACT_GELU_ERF, static_w=True)
             else:
-                h = ops.linear(h, mod.weight, mod.bias)
+                h = ops.linear(h, mod.weight, mod.bias, static_w=True)
         return h.view(B, N, -1)

@@ -160,16 +160,16 @@ class Qwen2ForCausalLM(nn.Module):
         x = inputs_embeds.to(self.dtype).contiguous().clone()
         for li, layer in enumerate(self.model.layers):
             h = ops.rmsnorm(x, layer.input_layernorm.weight, cfg.rms_norm_eps)
-            qkv = ops.linear(h, layer._qkv_w, layer._qkv_b)
+            qkv = ops.linear(h, layer._qkv_w, layer._qkv_b, static_w=True)
             ops.rope_kv_append(qkv, position_ids, Hq, Hkv, D, self.inv_freq, cache.k(li),
                                cache.v(li), cache.page_table, p0)
             q = qkv.view(S, Hq + 2 * Hkv, D)[:, :Hq]
             attn = ops.fmha(q, cache.k(li), cache.v(li), B=1, Sq=S, Sk=p0 + S, causal=True,
                             scale=D ** -0.5, page_table=cache.page_table)
-            ops.linear(attn.view(S, Hq * D), layer.self_attn.o_proj.weight, residual=x, out=x)
+            ops.linear(attn.view(S, Hq * D), layer.self_attn.o_proj.weight, residual=x, out=x, static_w=True)
             h = ops.rmsnorm(x, layer.post_attention_layernorm.weight, cfg.rms_norm_eps)
-            a = ops.linear(h, layer._gu_w, swiglu=True)
-            ops.linear(a, layer.mlp.down_proj.weight, residual=x, out=x)
+            a = ops.linear(h, layer._gu_w, swiglu=True, static_w=True)
+            ops.linear(a, layer.mlp.down_proj.weight, residual=x, out=x, static_w=True)
         cache.length = p0 + S
         return x
 
@@ -177,8 +177,8 @@ class Qwen2ForCausalLM(nn.Module):
         """final RMSNorm + lm_head for the given rows [R, hidden] -> [R, V] (bf16 like HF)."""
         h = ops.rmsnorm(hidden.contiguous().clone(), self.model.norm.weight, self.config.rms_norm_eps)
         if h.shape[0] == 1:
-            return ops.gemv(h[0], self.lm_head.weight).view(1, -1)
-        return ops.linear(h, self.lm_head.weight)
+            return ops.gemv(h[0], self.lm_head.weight, static_w=True).view(1, -1)
+        return ops.linear(h, self.lm_head.weight, static_w=True)
 
     def forward(self, inputs_embeds: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 position_ids: Optional[torch.Tensor] = None, past_key_values=None, labels=None,
@@ -365,16 +365,16 @@ class GraphDecoder:
         Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
         for li, layer in enumerate(llm.model.layers):
             ops.gemv(self.x, layer._qkv_w, bias=layer._qkv_b, norm_w=layer.input_layernorm.weight,
-                     norm_eps=cfg.rms_norm_eps, out=self.qkv)
+                     norm_eps=cfg.rms_norm_eps, out=self.qkv, static_w=True)
             ops.decode_attention(self.qkv, self.position, cache.k(li), cache.v(li), cache.page_table,
                                  self.attn, self.ws, self.counters, llm.inv_freq, Hq, Hkv, D,
                                  self.num_splits, D ** -0.5)
-            ops.gemv(self.attn, layer.self_attn.o_proj.weight, residual=self.x, out=self.x)
+            ops.gemv(self.attn, layer.self_attn.o_proj.weight, residual=self.x, out=self.x, static_w=True)
             ops.gemv(self.x, layer._gu_w, norm_w=layer.post_attention_layernorm.weight,
-                     norm_eps=cfg.rms_norm_eps, swiglu=True, out=self.act)
-            ops.gemv(self.act, layer.mlp.down_proj.weight, residual=self.x, out=self.x)
+                     norm_eps=cfg.rms_norm_eps, swiglu=True, out=self.act, static_w=True)
+            ops.gemv(self.act, layer.mlp.down_proj.weight, residual=self.x, out=self.x, static_w=True)
         ops.gemv(self.x, llm.lm_head.weight, norm_w=llm.model.norm.weight,
-                 norm_eps=cfg.rms_norm_eps, argmax_key=self.key, write_out=False)
+                 norm_eps=cfg.rms_norm_eps, argmax_key=self.key, write_out=False, static_w=True)
         ops.argmax_finalize(self.key, self.token, self.hist, self.step, self.position,
                             llm.model.embed_tokens.weight, self.x)
 
@@ -387,7 +387,7 @@ class GraphDecoder:
         self.position.fill_(cache.length - 1)  # finalize increments -> position of the new token
         self.x.copy_(last_hidden)
         ops.gemv(self.x, llm.lm_head.weight, norm_w=llm.model.norm.weight,
-                 norm_eps=cfg.rms_norm_eps, argmax_key=self.key, write_out=False)
+                 norm_eps=cfg.rms_norm_eps, argmax_key=self.key, write_out=False, static_w=True)
         ops.argmax_finalize(self.key, self.token, self.hist, self.step, self.position,
                             llm.model.embed_tokens.weight, self.x)
         self._started = 1

@@ -71,14 +71,14 @@ class SiglipEncoderLayer(nn.Module):
         C, H = cfg.hidden_size, cfg.num_attention_heads
         D = C // H
         h = ops.layernorm(x, self.layer_norm1.weight, self.layer_norm1.bias, cfg.layer_norm_eps)
-        qkv = ops.linear(h, self._qkv_w, self._qkv_b).view(B * S, 3, H, D)
+        qkv = ops.linear(h, self._qkv_w, self._qkv_b, static_w=True).view(B * S, 3, H, D)
         attn = ops.fmha(qkv[:, 0], qkv[:, 1], qkv[:, 2], B=B, Sq=S, Sk=S, causal=False,
                         scale=D ** -0.5)
         ops.linear(attn.view(B * S, C), self.self_attn.out_proj.weight, self.self_attn.out_proj.bias,
-                   residual=x, out=x)
+                   residual=x, out=x, static_w=True)
         h = ops.layernorm(x, self.layer_norm2.weight, self.layer_norm2.bias, cfg.layer_norm_eps)
-        f = ops.linear(h, self.mlp.fc1.weight, self.mlp.fc1.bias, act=ops.ACT_GELU_TANH)
-        ops.linear(f, self.mlp.fc2.weight, self.mlp.fc2.bias, residual=x, out=x)
+        f = ops.linear(h, self.mlp.fc1.weight, self.mlp.fc1.bias, act=ops.ACT_GELU_TANH, static_w=True)
+        ops.linear(f, self.mlp.fc2.weight, self.mlp.fc2.bias, residual=x, out=x, static_w=True)
         return x
 
 
@@ -130,7 +130,7 @@ class SiglipVisionModel(nn.Module):
         emb = self.vision_model.embeddings
         a = ops.patch_im2col(pixels.contiguous(), cfg.patch_size, self.k_pad)
         x = ops.linear(a, self._patch_w, emb.patch_embedding.bias,
-                       residual=emb.position_embedding.weight, res_row_mod=cfg.num_patches)
+                       residual=emb.position_embedding.weight, res_row_mod=cfg.num_patches, static_w=True)
         n_states = cfg.num_hidden_layers + 1
         idx = select_layer if select_layer >= 0 else n_states + select_layer
         for i in range(idx):

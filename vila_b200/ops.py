@@ -31,11 +31,26 @@ def _chk(t: torch.Tensor, name: str, dtype=torch.bfloat16) -> None:
         raise RuntimeError(f"vila_b200.ops: {name} must be {dtype}, got {t.dtype}")
 
 
+_WORKSPACE = {}
+
+
+def ensure_workspace(device, nbytes: int = 96 << 20) -> torch.Tensor:
+    """Allocate (once per device) and register the zero-initialised stream-K scratch."""
+    key = torch.device(device).index or 0
+    ws = _WORKSPACE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _WORKSPACE[key] = ws
+    check(_lib.load().vila_set_workspace(ws.data_ptr(), ws.numel()), "vila_set_workspace")
+    return ws
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
            act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, res_row_mod: int = 0,
            swiglu: bool = False, out: Optional[torch.Tensor] = None,
-           block_n: Optional[int] = None) -> torch.Tensor:
-    """out = epilogue(x @ w.T).  x [M,K] (row stride arbitrary), w [N,K]."""
+           block_n: Optional[int] = None, static_w: bool = False) -> torch.Tensor:
+    """out = epilogue(x @ w.T).  x [M,K] (row stride arbitrary), w [N,K].
+    static_w: w is a parameter (VILA_FLAG_STATIC_W): it may be fetched before the PDL wait."""
     _chk(x, "x"); _chk(w, "w")
     assert x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1], (x.shape, w.shape)
     assert x.stride(1) == 1 and w.stride(1) == 1
@@ -55,7 +70,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         ld_res = residual.stride(0)
     lib = _lib.load()
     args = (_p(x), x.stride(0), _p(w), w.stride(0), _p(bias), _p(residual), ld_res, res_row_mod,
-            _p(out), out.stride(0), M, N, K, act, 1 if swiglu else 0, _stream())
+            _p(out), out.stride(0), M, N, K, act, (1 if swiglu else 0) | (2 if static_w else 0), _stream())
     if block_n is None:
         check(lib.vila_linear(*args), "vila_linear")
     else:
@@ -214,7 +229,8 @@ def rope_kv_append(qkv: torch.Tensor, positions: torch.Tensor, Hq: int, Hkv: int
 
 def gemv(x: torch.Tensor, w: torch.Tensor, *, bias=None, norm_w=None, norm_eps: float = 1e-6,
          residual=None, swiglu: bool = False, out: Optional[torch.Tensor] = None,
-         argmax_key: Optional[torch.Tensor] = None, write_out: bool = True) -> Optional[torch.Tensor]:
+         argmax_key: Optional[torch.Tensor] = None, write_out: bool = True,
+         static_w: bool = False) -> Optional[torch.Tensor]:
     _chk(x, "x"); _chk(w, "w")
     N, K = w.shape
     assert x.numel() == K and w.is_contiguous()
@@ -224,7 +240,7 @@ def gemv(x: torch.Tensor, w: torch.Tensor, *, bias=None, norm_w=None, norm_eps: 
     p.x, p.w, p.bias, p.norm_w = _p(x), _p(w), _p(bias), _p(norm_w)
     p.norm_eps = norm_eps
     p.residual, p.y = _p(residual), _p(out)
-    p.N, p.K, p.swiglu = N, K, 1 if swiglu else 0
+    p.N, p.K, p.flags = N, K, (1 if swiglu else 0) | (2 if static_w else 0)
     p.argmax_key = _p(argmax_key)
     check(_lib.load().vila_gemv(C.byref(p), _stream()), "vila_gemv")
     return out

@@ -125,7 +125,7 @@ class SequenceParallelPrefill:
         n_local_pages = 2 * cp
         for li, layer in enumerate(llm.model.layers):
             h = ops.rmsnorm(x, layer.input_layernorm.weight, cfg.rms_norm_eps)
-            qkv = ops.linear(h, layer._qkv_w, layer._qkv_b)
+            qkv = ops.linear(h, layer._qkv_w, layer._qkv_b, static_w=True)
             kpool, vpool = pool[li, 0], pool[li, 1]
             # RoPE with GLOBAL positions; K/V rows land in this rank's region of the pool
             ops.rope_kv_append(qkv[:c], positions[:c], Hq, Hkv, D, llm.inv_freq, kpool, vpool,
@@ -144,10 +144,10 @@ class SequenceParallelPrefill:
                      page_table=page_table, out=attn[:c])
             ops.fmha(q[c:], kpool, vpool, B=1, Sq=c, Sk=b1, causal=True, scale=D ** -0.5,
                      page_table=page_table, out=attn[c:])
-            ops.linear(attn.view(2 * c, Hq * D), layer.self_attn.o_proj.weight, residual=x, out=x)
+            ops.linear(attn.view(2 * c, Hq * D), layer.self_attn.o_proj.weight, residual=x, out=x, static_w=True)
             h = ops.rmsnorm(x, layer.post_attention_layernorm.weight, cfg.rms_norm_eps)
-            a = ops.linear(h, layer._gu_w, swiglu=True)
-            ops.linear(a, layer.mlp.down_proj.weight, residual=x, out=x)
+            a = ops.linear(h, layer._gu_w, swiglu=True, static_w=True)
+            ops.linear(a, layer.mlp.down_proj.weight, residual=x, out=x, static_w=True)
         return x, pool
 
     @torch.inference_mode()
