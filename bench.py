@@ -133,7 +133,7 @@ def run_ours(args):
         emb, _, _ = model._embed(ids_h, {"image": [pixels_d]}, media_cfg, None, None)
         dec = llm.decoder(NEW_TOKENS)
         cache = dec.cache_for(emb.shape[1] + NEW_TOKENS)
-        hid = llm.prefill_hidden(emb[0], cache)
+        hid = llm.prefill_hidden_graphed(emb[0], cache)
         dec.start(hid[-1], cache)
         e1.record()
         dec.run(NEW_TOKENS)

@@ -23,7 +23,7 @@ for st in $STAGES; do
       timeout 600 python bench.py --impl reference --steps 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
       echo "== bench ref rc=$?"; tail -c 1500 gpurun_out/bench_ref.json ;;
     launches)
-      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none \
+      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none \
           --kernel-name-base demangled -k regex:vb:: -s 1450 -c 1500 --csv \
           --log-file gpurun_out/launches.csv python bench.py --profile --steps 1 > gpurun_out/launches.log 2>&1
       echo "== launches rc=$? lines=$(wc -l < gpurun_out/launches.csv)" ;;

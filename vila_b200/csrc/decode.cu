@@ -41,7 +41,7 @@ __device__ __forceinline__ uint32_t float_order(float f) {
 }
 
 template <int UNROLL>
-__global__ void __launch_bounds__(kGemvThreads, 1)
+__global__ void __launch_bounds__(kGemvThreads, 2)
 gemv_kernel(GemvParams p, int rows_per_block, int ksplit) {
   extern __shared__ uint4 smem_v[];
   uint4* xs = smem_v;                                              // K/8 vectors (bf16 x)
@@ -106,53 +106,77 @@ gemv_kernel(GemvParams p, int rows_per_block, int ksplit) {
   } else {
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) xs[i] = ldg_v4(xg + i);
   }
-  for (int i = threadIdx.x; i < nrows; i += blockDim.x) acc[i] = 0.f;
   if (threadIdx.x == 0) best_s = 0ull;
   __syncthreads();
 
   // ---- main loop: this warp's (row, k-part) items form ONE flat stream of 512-byte row chunks;
-  // UNROLL independent 128-bit loads per lane stay in flight across item boundaries ----
-  const int nchunks = (nvec + 31) >> 5;           // 32 vectors (256 elements) per chunk
+  // UNROLL independent 128-bit loads per lane stay in flight across item boundaries.  Item/chunk
+  // indices advance incrementally (no divisions on the load path).  Partial sums of the k-parts of a
+  // row go to separate slots and are added in a fixed order (deterministic). ----
+  const int nchunks = (nvec + 31) >> 5;             // 32 vectors (256 elements) per chunk
   const int cpi = (nchunks + ksplit - 1) / ksplit;  // chunks per item
   const int items = nrows * ksplit;
-  const int my_items = items > warp ? (items - warp + kGemvWarps - 1) / kGemvWarps : 0;
-  const int total = my_items * cpi;
-  float sum = 0.f;
-  for (int f0 = 0; f0 < total; f0 += UNROLL) {
-    uint4 wv[UNROLL];
-    int vidx[UNROLL];
+  {
+    int item = warp;                 // item being LOADED
+    int ch = 0;                      // chunk of that item
+    int r = item / ksplit, part = item - r * ksplit;
+    const uint4* wrow = reinterpret_cast<const uint4*>(p.w + static_cast<size_t>(row0 + r) * p.K);
+    int vbase = part * cpi * 32 + lane;
+    float sum = 0.f;
+    while (item < items) {
+      uint4 wv[UNROLL];
+      int xo[UNROLL];    // smem vector index of the matching x chunk, -1: nothing loaded
+      int fin[UNROLL];   // >= 0: this chunk closes an item -> slot index to publish
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int f = f0 + u;
-      const int it = f / cpi, ch = f - it * cpi;
-      const int item = warp + it * kGemvWarps;
-      const int r = item / ksplit, part = item - r * ksplit;
-      const int vi = (part * cpi + ch) * 32 + lane;
-      const bool ok = f < total && vi < nvec;
-      vidx[u] = ok ? vi : -1;
-      wv[u] = ok ? ldg_stream(reinterpret_cast<const uint4*>(p.w + static_cast<size_t>(row0 + r) * p.K) + vi)
-                 : make_uint4(0, 0, 0, 0);
-    }
+      for (int u = 0; u < UNROLL; ++u) {
+        const bool live = item < items;
+        const int vi = vbase + ch * 32;
+        const bool ok = live && vi < nvec;
+        xo[u] = ok ? vi : -1;
+        wv[u] = ok ? ldg_stream(wrow + vi) : make_uint4(0, 0, 0, 0);
+        fin[u] = (live && ch == cpi - 1) ? item : -1;
+        if (live) {
+          if (++ch == cpi) {
+            ch = 0;
+            item += kGemvWarps;
+            if (item < items) {
+              r = item / ksplit;
+              part = item - r * ksplit;
+              wrow = reinterpret_cast<const uint4*>(p.w + static_cast<size_t>(row0 + r) * p.K);
+              vbase = part * cpi * 32 + lane;
+            }
+          }
+        }
+      }
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int f = f0 + u;
-      if (f < total) {  // warp-uniform
-        if (vidx[u] >= 0) sum = dot8(wv[u], xs[vidx[u]], sum);
-        const int it = f / cpi, ch = f - it * cpi;
-        if (ch == cpi - 1) {  // item finished: reduce and publish
+      for (int u = 0; u < UNROLL; ++u) {
+        if (xo[u] >= 0) sum = dot8(wv[u], xs[xo[u]], sum);
+        if (fin[u] >= 0) {  // warp-uniform
           const float tot = warp_sum(sum);
           sum = 0.f;
-          if (lane == 0) {
-            const int item = warp + it * kGemvWarps;
-            const int r = item / ksplit;
-            if (ksplit == 1) acc[r] = tot;
-            else atomicAdd(&acc[r], tot);
-          }
+          if (lane == 0) acc[fin[u]] = tot;  // slot = row * ksplit + part
         }
       }
     }
   }
   __syncthreads();
+  if (ksplit > 1) {  // fixed-order reduction of the k-parts
+    float tot[4];
+    int nmine = 0;
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+      float t = 0.f;
+      for (int q = 0; q < ksplit; ++q) t += acc[i * ksplit + q];
+      if (nmine < 4) tot[nmine] = t;
+      ++nmine;
+    }
+    __syncthreads();
+    nmine = 0;
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+      if (nmine < 4) acc[i] = tot[nmine];
+      ++nmine;
+    }
+    __syncthreads();
+  }
 
   // ---- epilogue ----
   if (p.flags & 1) {
@@ -421,7 +445,7 @@ int gemv_bf16(const GemvParams& p, cudaStream_t stream) {
   const int nchunks = ((p.K >> 3) + 31) >> 5;
   int ksplit = 1;
   while (rows_per_block * ksplit < 3 * kGemvWarps && ksplit * 2 <= nchunks && ksplit < 16) ksplit *= 2;
-  const size_t smem = static_cast<size_t>((p.K + 7) / 8) * 16 + static_cast<size_t>(rows_per_block) * 4;
+  const size_t smem = static_cast<size_t>((p.K + 7) / 8) * 16 + static_cast<size_t>(rows_per_block) * ksplit * 4;
   VB_CHECK(smem <= 200 * 1024, "gemv: K=%d / rows_per_block=%d exceed shared memory", p.K,
            rows_per_block);
   auto kern = gemv_kernel<8>;

@@ -8,8 +8,8 @@
 //     bias / GELU / SwiGLU / residual (+ broadcast "row modulo" residual for position embeddings)
 //   * scheduling: data-parallel over output tiles, or STREAM-K when the tile count does not fill the
 //     148 SMs evenly (skinny prefill GEMMs, M = 280): the (tile, k-block) iteration space is cut
-//     into equal contiguous ranges, partial tiles are reduced with red.global.add.v4.f32 into an
-//     fp32 workspace and the last-arriving CTA applies the epilogue (self-cleaning workspace)
+//     into equal contiguous ranges, each partial tile is parked in its own fp32 workspace slot and
+//     the last-arriving CTA sums the slots in a fixed order (deterministic) and applies the epilogue
 //   * programmatic dependent launch: barrier init / TMEM alloc / descriptor prefetch and — for
 //     parameter matrices — the first pipeline stages of W overlap the predecessor kernel's tail
 //
@@ -51,11 +51,6 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
-               "f"(d)
-               : "memory");
-}
 __device__ __forceinline__ float4 ld_cg_v4(const float* p) {
   float4 r;
   asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -258,22 +253,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const bool partial = (kb0 != 0) || (kb1 != sch.nkb);
       bool finalize = true;       // apply the epilogue and write C
       bool from_ws = false;       // accumulator comes from the fp32 workspace
+      int n_slots = 0;
+      const float* slot0 = nullptr;  // first partial slot of this tile, this thread's row
       if (partial) {
-        // ---- stream-K partial tile: reduce into the fp32 workspace ----
+        // ---- stream-K partial tile: park the fp32 partial in this segment's own workspace slot
+        // (slots are summed later in a fixed order -> deterministic, no atomics on data) ----
+        const long total = static_cast<long>(sch.num_tiles) * sch.nkb;
+        const long i0 = static_cast<long>(t) * sch.nkb;
+        auto cta_of = [&](long i) {
+          long g = i * gridDim.x / total;
+          while (g + 1 < static_cast<long>(gridDim.x) && total * (g + 1) / gridDim.x <= i) ++g;
+          return static_cast<int>(g);
+        };
+        const int c_first = cta_of(i0);
+        n_slots = cta_of(i0 + sch.nkb - 1) - c_first + 1;
+        const int my_slot = static_cast<int>(blockIdx.x) - c_first;
+        const size_t tile_base = static_cast<size_t>(t) * epi.split_k * (BLOCK_M * BLOCK_N);
+        const size_t row_off = static_cast<size_t>(quad * 32 + lane) * BLOCK_N;
+        slot0 = epi.splitk_ws + tile_base + row_off;
+        float* mine = epi.splitk_ws + tile_base + static_cast<size_t>(my_slot) * (BLOCK_M * BLOCK_N) + row_off;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_row + c * 32, r);
           tmem_ld_wait();
-          const int n0 = n_blk * BLOCK_N + c * 32;
           if (row_ok) {
-            float* wsp = epi.splitk_ws + static_cast<size_t>(row) * N + n0;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              if (n0 + g * 4 < N)
-                red_add_v4(wsp + g * 4, __uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                           __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
-            }
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<uint4*>(mine + c * 32 + g * 4) =
+                  make_uint4(r[g * 4 + 0], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]);
           }
         }
         tc_fence_before();
@@ -314,13 +322,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
             if (row_ok) {
-              float* wsp = epi.splitk_ws + static_cast<size_t>(row) * N + n0;
+              for (int s = 0; s < n_slots; ++s) {  // fixed order: slot 0 (lowest k) first
+                const float* wsp = slot0 + static_cast<size_t>(s) * (BLOCK_M * BLOCK_N) + c * 32;
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                if (n0 + g * 4 < N) {
+                for (int g = 0; g < 8; ++g) {
                   const float4 q = ld_cg_v4(wsp + g * 4);
-                  v[g * 4 + 0] = q.x; v[g * 4 + 1] = q.y; v[g * 4 + 2] = q.z; v[g * 4 + 3] = q.w;
-                  *reinterpret_cast<float4*>(wsp + g * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                  v[g * 4 + 0] += q.x; v[g * 4 + 1] += q.y; v[g * 4 + 2] += q.z; v[g * 4 + 3] += q.w;
                 }
               }
             }
@@ -443,8 +450,12 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
   const int nkb = (K + BLOCK_K - 1) / BLOCK_K;
   // stream-K when whole tiles would leave SMs idle or produce a ragged last wave
   bool sk = false;
-  const size_t need = kCounterBytes + static_cast<size_t>(M) * N * 4;
-  const bool ws_ok = g_ws.ptr != nullptr && g_ws.bytes >= need && tiles <= 16384 && N % 4 == 0;
+  const long total_it = static_cast<long>(tiles) * nkb;
+  const int sk_grid = total_it < sms ? static_cast<int>(total_it) : sms;
+  const long ipc = total_it / sk_grid;  // k-iterations per CTA (floor)
+  const int max_slots = static_cast<int>((nkb + ipc - 1) / ipc) + 1;
+  const size_t need = kCounterBytes + static_cast<size_t>(tiles) * max_slots * BLOCK_M * BLOCK_N * 4;
+  const bool ws_ok = g_ws.ptr != nullptr && g_ws.bytes >= need && tiles <= 16384;
   if (force_stream_k >= 0) {
     sk = force_stream_k != 0;
   } else if (ws_ok && nkb >= 4 && tiles % sms != 0 && tiles < 4 * sms) {
@@ -460,9 +471,8 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
   int grid = tiles < sms ? tiles : sms;
   epi.split_k = 1;
   if (sk) {
-    const long total = static_cast<long>(tiles) * nkb;
-    grid = total < sms ? static_cast<int>(total) : sms;
-    epi.split_k = 2;  // any value > 1 selects the stream-K schedule
+    grid = sk_grid;
+    epi.split_k = max_slots;  // > 1 selects the stream-K schedule; = workspace slots per tile
     epi.splitk_counters = static_cast<int*>(g_ws.ptr);
     epi.splitk_ws = reinterpret_cast<float*>(static_cast<char*>(g_ws.ptr) + kCounterBytes);
   }

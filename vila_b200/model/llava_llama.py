@@ -198,6 +198,7 @@ class LlavaLlamaModel(nn.Module):
             self.encoders["video"] = BasicVideoEncoder(self)
         self.generation_config = None
         self.training = False
+        self._vision_graphs = {}
 
     # ---- reference accessors (llava_arch.py:206-226) ----
     def get_llm(self):
@@ -292,7 +293,26 @@ class LlavaLlamaModel(nn.Module):
             block_sizes = [None] * len(images)
         tower, proj = self.get_vision_tower(), self.get_mm_projector()
         if not getattr(self.config, "dynamic_s2", False):
-            return proj(tower(images))
+            # tower + projector replayed from a CUDA graph cached per input shape (~190 launches per
+            # call otherwise issued one by one from Python)
+            key = tuple(images.shape)
+            ent = self._vision_graphs.get(key)
+            if ent is None:
+                if len(self._vision_graphs) >= 4:
+                    self._vision_graphs.pop(next(iter(self._vision_graphs)))
+                static_in = torch.empty(key, dtype=self.dtype, device=self.device)
+                static_in.copy_(images)
+                proj(tower(static_in))  # warm-up
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    static_out = proj(tower(static_in))
+                ent = (g, static_in, static_out)
+                self._vision_graphs[key] = ent
+            g, static_in, static_out = ent
+            static_in.copy_(images, non_blocking=True)
+            g.replay()
+            return static_out
         feats = tower(images)  # [n_tiles, N, C]
         scales = tower.scales
         idx = tower.resize_output_to_scale_idx
