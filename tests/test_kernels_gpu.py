@@ -353,8 +353,10 @@ def test_rope_kv_append(cuda):
 # ------------------------------------------------------------------------------------------------
 # decode kernels
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("N,K", [(4608, 3584), (3584, 3584), (3584, 18944), (512, 2048), (1000, 1536)])
-def test_gemv_bias_residual_norm(cuda, N, K):
+@pytest.mark.parametrize("variant", [0, 1])  # 0: TMA-ring kernel, 1: register-staged kernel
+@pytest.mark.parametrize("N,K", [(4608, 3584), (3584, 3584), (3584, 18944), (512, 2048), (1000, 1536),
+                                 (152064, 3584), (37888, 3584), (64, 512)])
+def test_gemv_bias_residual_norm(cuda, N, K, variant):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(N + K)
     x = bf(torch.randn(K, device=cuda, generator=g))
@@ -362,16 +364,18 @@ def test_gemv_bias_residual_norm(cuda, N, K):
     b = bf(torch.randn(N, device=cuda, generator=g))
     r = bf(torch.randn(N, device=cuda, generator=g))
     nw = bf(torch.randn(K, device=cuda, generator=g))
-    out = ops.gemv(x, w, bias=b, residual=r)
+    out = ops.gemv(x, w, bias=b, residual=r, variant=variant, static_w=True)
+    assert torch.equal(out, ops.gemv(x, w, bias=b, residual=r, variant=variant))  # deterministic
     ref = rb(rb(w.float() @ x.float() + b.float()) + r.float())
     assert rel_err(out, ref) < 1e-2
-    out = ops.gemv(x, w, norm_w=nw, norm_eps=1e-6)
+    out = ops.gemv(x, w, norm_w=nw, norm_eps=1e-6, variant=variant)
     xn = O.rms_norm(x[None], nw, 1e-6)[0]
     ref = w.float() @ xn.float()
     assert rel_err(out, ref) < 1e-2
 
 
-def test_gemv_swiglu(cuda):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_gemv_swiglu(cuda, variant):
     ops = _ops()
     I, K = 18944, 3584
     g = torch.Generator(device="cuda").manual_seed(21)
@@ -379,7 +383,7 @@ def test_gemv_swiglu(cuda):
     wg = bf(torch.randn(I, K, device=cuda, generator=g) / math.sqrt(K))
     wu = bf(torch.randn(I, K, device=cuda, generator=g) / math.sqrt(K))
     w = torch.stack([wg, wu], dim=1).reshape(2 * I, K).contiguous()
-    out = ops.gemv(x, w, swiglu=True)
+    out = ops.gemv(x, w, swiglu=True, variant=variant, static_w=True)
     ref = rb(rb(F.silu(rb(wg.float() @ x.float()))) * rb(wu.float() @ x.float()))
     assert rel_err(out, ref) < 1e-2
 

@@ -26,6 +26,7 @@ SOURCES = [
     "norm.cu",
     "data_movement.cu",
     "decode.cu",
+    "gemv_tma.cu",
 ]
 HEADERS = ["common.cuh", "kernels.h", "../../include/vila_b200.h"]
 

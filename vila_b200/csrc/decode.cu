@@ -438,6 +438,10 @@ decode_attn_kernel(DecodeAttnParams p) {
 int gemv_bf16(const GemvParams& p, cudaStream_t stream) {
   VB_CHECK(p.N > 0 && p.K > 0 && p.K % 8 == 0, "gemv: bad shape N=%d K=%d (K %% 8 == 0)", p.N, p.K);
   VB_CHECK(!(p.flags & 1) || p.N % 2 == 0, "gemv: swiglu needs even N");
+  if (!(p.flags & 4)) {  // default: TMA-ring kernel; flag 4 selects the register-staged variant
+    const int rc = gemv_tma_bf16(p, stream);
+    if (rc >= 0) return rc;
+  }
   const int sms = num_sms();
   int rows_per_block = (p.N + sms - 1) / sms;
   if ((p.flags & 1) && (rows_per_block & 1)) rows_per_block += 1;

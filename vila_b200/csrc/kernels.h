@@ -98,11 +98,12 @@ struct GemvParams {
   const __nv_bfloat16* residual;  // [N] or null (added after bias)
   __nv_bfloat16* y;               // [N] (or [N/2] with swiglu)
   int N, K;
-  int flags;   // bit0: SwiGLU (rows interleaved gate, up); bit1: weights are static (L2 prefetch before PDL wait)
+  int flags;   // bit0: SwiGLU (rows interleaved gate, up); bit1: weights are static (stream before the PDL wait); bit2: force the register-staged kernel
   // optional fused greedy argmax over y (lm_head): 64-bit packed (value, ~index) max-reduction
   unsigned long long* argmax_key;
 };
 int gemv_bf16(const GemvParams& p, cudaStream_t stream);
+int gemv_tma_bf16(const GemvParams& p, cudaStream_t stream);  // -1: shape not supported
 // token = argmax key; token_hist[step++] = token; position++; key = 0; x_next = embed_table[token]
 int argmax_finalize(unsigned long long* key, int32_t* token_out, int32_t* token_hist,
                     int32_t* step_counter, int32_t* position, const __nv_bfloat16* embed_table,

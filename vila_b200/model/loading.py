@@ -69,14 +69,21 @@ def load_pretrained(model_path: str, device="cuda") -> LlavaLlamaModel:
     d = Path(model_path)
     cfg = config_from_dir(d)
     tok = None
-    try:  # a real checkpoint ships the tokenizer next to the LLM
-        from transformers import AutoTokenizer
-        tok = AutoTokenizer.from_pretrained(str(d / "llm"))
-        tok.media_token_ids = {"image": tok.convert_tokens_to_ids("<image>"),
-                               "video": tok.convert_tokens_to_ids("<vila/video>")}
-        tok.stop_token_ids = [tok.eos_token_id]
-    except Exception:
-        tok = None
+    has_tok_files = any((d / "llm" / f).exists() for f in ("tokenizer.json", "vocab.json",
+                                                            "tokenizer_config.json"))
+    if has_tok_files:  # a real checkpoint ships the tokenizer next to the LLM
+        try:
+            from transformers import AutoTokenizer
+            tok = AutoTokenizer.from_pretrained(str(d / "llm"))
+            ids = {"image": tok.convert_tokens_to_ids("<image>"),
+                   "video": tok.convert_tokens_to_ids("<vila/video>")}
+            if not all(isinstance(v, int) and v >= 0 for v in ids.values()):
+                raise ValueError("media tokens missing from the tokenizer")
+            tok.media_token_ids = ids
+            tok.stop_token_ids = [tok.eos_token_id]
+            cfg.image_token_id, cfg.video_token_id = ids["image"], ids["video"]
+        except Exception:
+            tok = None
     model = LlavaLlamaModel(cfg, device=device, tokenizer=tok)
     sd = {}
     sd.update({"llm." + k: v for k, v in _load_dir_tensors(d / "llm").items()})

@@ -230,7 +230,7 @@ def rope_kv_append(qkv: torch.Tensor, positions: torch.Tensor, Hq: int, Hkv: int
 def gemv(x: torch.Tensor, w: torch.Tensor, *, bias=None, norm_w=None, norm_eps: float = 1e-6,
          residual=None, swiglu: bool = False, out: Optional[torch.Tensor] = None,
          argmax_key: Optional[torch.Tensor] = None, write_out: bool = True,
-         static_w: bool = False) -> Optional[torch.Tensor]:
+         static_w: bool = False, variant: int = 0) -> Optional[torch.Tensor]:
     _chk(x, "x"); _chk(w, "w")
     N, K = w.shape
     assert x.numel() == K and w.is_contiguous()
@@ -240,7 +240,7 @@ def gemv(x: torch.Tensor, w: torch.Tensor, *, bias=None, norm_w=None, norm_eps: 
     p.x, p.w, p.bias, p.norm_w = _p(x), _p(w), _p(bias), _p(norm_w)
     p.norm_eps = norm_eps
     p.residual, p.y = _p(residual), _p(out)
-    p.N, p.K, p.flags = N, K, (1 if swiglu else 0) | (2 if static_w else 0)
+    p.N, p.K, p.flags = N, K, (1 if swiglu else 0) | (2 if static_w else 0) | (4 if variant == 1 else 0)
     p.argmax_key = _p(argmax_key)
     check(_lib.load().vila_gemv(C.byref(p), _stream()), "vila_gemv")
     return out
