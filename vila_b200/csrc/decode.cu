@@ -8,6 +8,7 @@
 //  decode_attn_kernel  split-KV paged attention for GQA (7 query heads share one KV head), with
 //                    RoPE of q / new k and the KV append fused in (replaces apply_rotary_pos_emb,
 //                    DynamicCache.update (torch.cat) and flash_attn decode).
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -253,7 +254,7 @@ constexpr int kDaThreads = 256;
 constexpr int kDaWarps = 8;
 constexpr int kMaxG = 8;  // query heads per kv head
 
-template <int D, int G>
+template <int D, int G, bool kCluster>
 __global__ void __launch_bounds__(kDaThreads)
 decode_attn_kernel(DecodeAttnParams p) {
   const float* __restrict__ inv_freq = p.inv_freq;
@@ -385,6 +386,49 @@ decode_attn_kernel(DecodeAttnParams p) {
     for (int e = 0; e < VPT; ++e) red_o[slot][g][dl * VPT + e] = o_acc[g][e];
   }
   __syncthreads();
+  // ---- cross-split combine ----
+  if constexpr (kCluster) {
+    // All splits of this KV head form one thread-block cluster: block partials stay in shared
+    // memory and are combined through DSMEM (no global workspace / atomics / fences).
+    namespace cg = cooperative_groups;
+    __shared__ float part_m[G], part_l[G];
+    __shared__ float part_o[G][D];
+    for (int idx = threadIdx.x; idx < G * D; idx += blockDim.x) {
+      const int g = idx / D, d = idx % D;
+      float mm = -INFINITY;
+      for (int s = 0; s < kDaWarps * 2; ++s) mm = fmaxf(mm, red_m[s][g]);
+      float ll = 0.f, oo = 0.f;
+      for (int s = 0; s < kDaWarps * 2; ++s) {
+        const float w = (red_m[s][g] == -INFINITY) ? 0.f : exp2f(red_m[s][g] - mm);
+        ll += red_l[s][g] * w;
+        oo += red_o[s][g][d] * w;
+      }
+      if (d == 0) {
+        part_m[g] = mm;
+        part_l[g] = ll;
+      }
+      part_o[g][d] = oo;
+    }
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    const int nr = static_cast<int>(cluster.num_blocks());
+    const int rank = static_cast<int>(cluster.block_rank());
+    for (int idx = rank * blockDim.x + threadIdx.x; idx < G * D; idx += nr * blockDim.x) {
+      const int g = idx / D, d = idx % D;
+      float mm = -INFINITY;
+      for (int s = 0; s < nr; ++s) mm = fmaxf(mm, cluster.map_shared_rank(&part_m[0], s)[g]);
+      float ll = 0.f, oo = 0.f;
+      for (int s = 0; s < nr; ++s) {
+        const float ms = cluster.map_shared_rank(&part_m[0], s)[g];
+        const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
+        ll += cluster.map_shared_rank(&part_l[0], s)[g] * w;
+        oo += cluster.map_shared_rank(&part_o[0][0], s)[g * D + d] * w;
+      }
+      p.out[(hk * G + g) * D + d] = __float2bfloat16(oo / ll);
+    }
+    cluster.sync();  // peers may still be reading this CTA's shared memory
+    return;
+  }
   // thread -> (g, d) pairs
   float* ws_m = p.ws;                                             // [Hkv][splits][G]
   float* ws_l = ws_m + p.Hkv * p.num_splits * G;                  // [Hkv][splits][G]
@@ -481,14 +525,16 @@ int decode_attention(const DecodeAttnParams& p, cudaStream_t stream) {
   dim3 grid(p.Hkv, p.num_splits);
 #define VB_DA_CASE(GG)                                                                          \
   case GG: {                                                                                    \
-    auto kern = decode_attn_kernel<128, GG>;                                                    \
+    const bool use_cluster = p.num_splits <= 8;                                                 \
+    auto kern = use_cluster ? decode_attn_kernel<128, GG, true> : decode_attn_kernel<128, GG, false>; \
     const size_t smem = (size_t)kDaWarps * 2 * GG * (128 + 2) * sizeof(float);                  \
-    static bool attr_done = false;                                                              \
-    if (!attr_done) {                                                                           \
+    static bool attr_done[2] = {false, false};                                                  \
+    if (!attr_done[use_cluster]) {                                                              \
       VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_done = true;                                                                         \
+      attr_done[use_cluster] = true;                                                            \
     }                                                                                           \
-    VB_CUDA(launch_pdl(kern, grid, dim3(kDaThreads), smem, stream, p));                         \
+    VB_CUDA(launch_pdl_cluster(kern, grid, dim3(kDaThreads), smem, stream,                      \
+                               dim3(1, use_cluster ? p.num_splits : 1, 1), p));                 \
     break;                                                                                      \
   }
   switch (G) {

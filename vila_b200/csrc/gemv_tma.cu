@@ -59,7 +59,7 @@ struct TmaGemvLayout {
   int x_off, acc_off, ring_off, bar_off, total;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gemv_tma_kernel(GemvParams p, int rows_per_block, int ksplit, TmaGemvLayout L) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint4* xs = reinterpret_cast<uint4*>(smem + L.x_off);
@@ -170,14 +170,19 @@ gemv_tma_kernel(GemvParams p, int rows_per_block, int ksplit, TmaGemvLayout L) {
     }
   }
   __syncthreads();
-  if (ksplit > 1) {  // fixed-order reduction of the k-parts (nrows * ksplit is small here)
-    float tot = 0.f;
-    const int i = threadIdx.x;
-    if (i < nrows)
-      for (int q = 0; q < ksplit; ++q) tot += acc[i * ksplit + q];
-    __syncthreads();
-    if (i < nrows) acc[i] = tot;
-    __syncthreads();
+  if (ksplit > 1) {
+    // fixed-order reduction of the k-parts, in place: acc[i] <- sum_q acc[i*ksplit + q].  Rows are
+    // processed in phases of blockDim.x; writing row i only overwrites slots of rows <= i, which
+    // have been read in this or an earlier phase.
+    for (int base = 0; base < nrows; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      float tot = 0.f;
+      if (i < nrows)
+        for (int q = 0; q < ksplit; ++q) tot += acc[i * ksplit + q];
+      __syncthreads();
+      if (i < nrows) acc[i] = tot;
+      __syncthreads();
+    }
   }
 
   // ---- epilogue ----
@@ -228,32 +233,44 @@ int gemv_tma_bf16(const GemvParams& p, cudaStream_t stream) {
   int rows_per_block = (p.N + sms - 1) / sms;
   if ((p.flags & 1) && (rows_per_block & 1)) rows_per_block += 1;
   const int grid = (p.N + rows_per_block - 1) / rows_per_block;
-  // choose ksplit: chunk <= 8 KiB, (K/ksplit) % 8 == 0, and >= ~6 items per warp when possible
-  int best_ks = -1;
-  for (int ks = 1; ks <= 64; ++ks) {
+  // Shared-memory budget: HALF an SM, so that the next kernel's CTA can become resident next to this
+  // one (programmatic dependent launch) and stream its weights while this kernel is still running —
+  // the HBM pipe then stays full across kernel boundaries.
+  constexpr int kSmemBudget = 106 * 1024;
+  const int x_bytes = (p.K * 2 + 127) / 128 * 128;
+  TmaGemvLayout L;
+  int ksplit = -1;
+  for (int ks = 1; ks <= 128; ++ks) {
     if (p.K % ks) continue;
     const int ce = p.K / ks;
     if (ce % 8) continue;
-    if (ce * 2 > 8192) continue;
-    if (ce * 2 < 1024 && best_ks > 0) break;
-    best_ks = ks;
-    if (static_cast<long>(rows_per_block) * ks >= 6L * kWarps) break;
+    const int cb = ce * 2;
+    if (cb > 8192) continue;
+    if (cb < 512) break;
+    const int acc_bytes = (rows_per_block * ks * 4 + 127) / 128 * 128;
+    const int ring_budget = kSmemBudget - x_bytes - acc_bytes - kWarps * kMaxStages * 8 - 256;
+    int st = ring_budget / (kWarps * cb);
+    if (st > kMaxStages) st = kMaxStages;
+    if (st < 3) continue;  // need a few chunks in flight per warp
+    ksplit = ks;
+    L.stages = st;
+    if (static_cast<long>(rows_per_block) * ks >= 6L * kWarps) break;  // enough items per warp
   }
-  if (best_ks < 0) return -1;
-  const int ksplit = best_ks;
-  if (ksplit > 1 && rows_per_block > kThreads) return -1;  // fixed-order reduce uses one thread per row
-  TmaGemvLayout L;
+  if (ksplit < 0) return -1;
   L.chunk_elems = p.K / ksplit;
   const int chunk_bytes = L.chunk_elems * 2;
   L.x_off = 0;
-  L.acc_off = (p.K * 2 + 127) / 128 * 128;
+  L.acc_off = x_bytes;
   L.ring_off = (L.acc_off + rows_per_block * ksplit * 4 + 127) / 128 * 128;
-  const int budget = 220 * 1024 - L.ring_off - kWarps * kMaxStages * 8 - 256;
-  int stages = budget / (kWarps * chunk_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return -1;
-  L.stages = stages;
-  L.bar_off = (L.ring_off + kWarps * stages * chunk_bytes + 127) / 128 * 128;
+  {
+    // recompute stages for the final ksplit (the loop may have broken on an earlier candidate)
+    const int ring_budget = kSmemBudget - L.ring_off - kWarps * kMaxStages * 8 - 256;
+    int st = ring_budget / (kWarps * chunk_bytes);
+    if (st > kMaxStages) st = kMaxStages;
+    if (st < 2) return -1;
+    L.stages = st;
+  }
+  L.bar_off = (L.ring_off + kWarps * L.stages * chunk_bytes + 127) / 128 * 128;
   L.total = L.bar_off + kWarps * kMaxStages * 8;
   static bool attr = false;
   if (!attr) {
