@@ -458,11 +458,9 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
   const bool ws_ok = g_ws.ptr != nullptr && g_ws.bytes >= need && tiles <= 16384;
   if (force_stream_k >= 0) {
     sk = force_stream_k != 0;
-  } else if (ws_ok && nkb >= 4 && tiles % sms != 0 && tiles < 4 * sms) {
-    const int waves = (tiles + sms - 1) / sms;
-    const double eff = static_cast<double>(tiles) / (static_cast<double>(waves) * sms);
-    sk = eff < 0.9;
   }
+  // (stream-K stays opt-in: on the NVILA shapes the partial-tile fix-up costs more than the SM
+  //  under-fill it removes — see profiles/r01_gemm_configs.md)
   if (sk && !ws_ok) {
     set_last_error("gemm: stream-K needs a registered workspace of >= %zu bytes (vila_set_workspace)",
                    need);
@@ -511,10 +509,13 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
   if (check_args(A, lda, W, ldw, C, ldc, M, N, K, epi)) return 1;
   // Tile-shape heuristic. N=256 tiles keep the MMA (not shared-memory bandwidth) the limiter when
   // there is enough work; N=128 otherwise; stream-K (inside launch_gemm) fixes SM under-fill.
+  // Measured on B200 (tools/bench_gemm.py): 128x256 tiles win as soon as they fill ~70 % of the
+  // SMs (the 256-wide tile keeps the MMA, not shared-memory bandwidth, the limiter); otherwise
+  // 128x128; 64-wide tiles only for narrow outputs.
   const int sms = num_sms();
   const int mb = (M + BLOCK_M - 1) / BLOCK_M;
   const long tiles256 = static_cast<long>(mb) * ((N + 255) / 256);
-  if (tiles256 >= 2L * sms && N % 256 == 0)
+  if (tiles256 * 10 >= 7L * sms)
     return launch_gemm<256, 4>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
   if (N < 128) return launch_gemm<64, 8>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
   return launch_gemm<128, 6>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);

@@ -59,7 +59,7 @@ struct TmaGemvLayout {
   int x_off, acc_off, ring_off, bar_off, total;
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 gemv_tma_kernel(GemvParams p, int rows_per_block, int ksplit, TmaGemvLayout L) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint4* xs = reinterpret_cast<uint4*>(smem + L.x_off);
@@ -233,10 +233,11 @@ int gemv_tma_bf16(const GemvParams& p, cudaStream_t stream) {
   int rows_per_block = (p.N + sms - 1) / sms;
   if ((p.flags & 1) && (rows_per_block & 1)) rows_per_block += 1;
   const int grid = (p.N + rows_per_block - 1) / rows_per_block;
-  // Shared-memory budget: HALF an SM, so that the next kernel's CTA can become resident next to this
-  // one (programmatic dependent launch) and stream its weights while this kernel is still running —
-  // the HBM pipe then stays full across kernel boundaries.
-  constexpr int kSmemBudget = 106 * 1024;
+  // Shared-memory budget: (almost) the whole SM.  Measured on B200: under a saturated HBM pipe the
+  // load latency is ~2.5 us, so ~110+ KB must be in flight per SM to sustain the full rate; halving
+  // the rings to let the next kernel's CTA co-reside (PDL) dropped the gate/up GEMV from 97 % to
+  // 76 % of the measured HBM peak (profiles/r01_gemv_variants.md).
+  constexpr int kSmemBudget = 220 * 1024;
   const int x_bytes = (p.K * 2 + 127) / 128 * 128;
   TmaGemvLayout L;
   int ksplit = -1;
