@@ -360,6 +360,109 @@ def cpu_baseline_sample(cfg, threads=None, seconds_budget=20.0):
                       "layers at S=280 the same way" % n_tok}
 
 
+def run_sp(args):
+    """BASELINE.json configs[4]: LongVILA-8B, `--frames` synthetic frames (default 256), vision tower
+    sharded by frames, zigzag sequence-parallel prefill with one in-place KV all-gather per layer.
+    STRONG scaling: the same video is processed by N GPUs; value = prompt tokens / max-over-ranks time."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from vila_b200 import sp
+    from vila_b200.model import LlavaLlamaModel, nvila_video_8b
+
+    cfg = nvila_video_8b()
+    model = LlavaLlamaModel(cfg, device="cuda").init_random(0, device_rng=True)
+    llm = model.llm
+    F = args.frames
+    f0, f1 = sp.shard_frames(F, world, rank)
+    g = torch.Generator(device="cuda").manual_seed(100 + rank)
+    S_img = cfg.vision_tower_cfg.image_size
+    frames = torch.randn(f1 - f0, 3, S_img, S_img, device="cuda", generator=g).to(torch.bfloat16)
+    n_text = 22
+    text_ids = torch.randint(0, 151643, (n_text,), generator=torch.Generator().manual_seed(7))
+    tok_per_frame = 256 + 1
+    S = F * tok_per_frame + n_text
+    plan = sp.make_plan(S, world, rank)
+    runner = sp.SequenceParallelPrefill(llm)
+    pool = runner.new_pool(plan)
+    newline = llm.model.embed_tokens(torch.tensor(list(cfg.newline_token_ids), device="cuda"))
+    text_emb = llm.model.embed_tokens(text_ids.cuda())
+    per = (F + world - 1) // world
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step():
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        feats = []
+        for i in range(0, f1 - f0, 32):  # vision tower + projector on this rank's frames
+            feats.append(model.encode_images(frames[i:i + 32]).clone())
+        feats = torch.cat(feats) if feats else torch.empty(0, 256, cfg.hidden_size, device="cuda", dtype=torch.bfloat16)
+        local_emb = torch.cat([feats, newline[None].expand(feats.shape[0], -1, -1)], dim=1)
+        padded_local = torch.zeros(per, tok_per_frame, cfg.hidden_size, device="cuda", dtype=torch.bfloat16)
+        padded_local[:local_emb.shape[0]] = local_emb
+        e1.record()
+        if world > 1:  # every rank needs the full embedding sequence to cut its zigzag chunks
+            allf = torch.empty(world * per, tok_per_frame, cfg.hidden_size, device="cuda", dtype=torch.bfloat16)
+            dist.all_gather_into_tensor(allf, padded_local)
+        else:
+            allf = padded_local
+        seq = torch.zeros(plan.padded_len, cfg.hidden_size, device="cuda", dtype=torch.bfloat16)
+        seq[:F * tok_per_frame] = allf[:F].reshape(-1, cfg.hidden_size)
+        seq[F * tok_per_frame:S] = text_emb
+        local_rows = plan.extract_local(seq)
+        e2.record()
+        hid, _ = runner.prefill_hidden(local_rows, plan, pool)
+        logits = runner.last_token_logits(hid, plan)
+        tok = int(torch.argmax(logits.float()))
+        e3.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), tok
+
+    for _ in range(max(1, min(args.warmup, 3)) if args.profile else max(3, args.warmup)):
+        step()
+    dist.barrier(); torch.cuda.synchronize()
+    rows = []
+    with ClockSampler(local) as clocks:
+        for _ in range(args.steps):
+            rows.append(step())
+        dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([[r[0], r[1], r[2]] for r in rows], device="cuda", dtype=torch.float64).mean(0)
+    tot = t.sum().reshape(1)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(tot)
+        lc = cfg.llm_cfg
+        gemm_flops = 2.0 * 6.525e9 * S
+        attn_flops = 2.0 * S * S * lc.num_attention_heads * lc.head_dim * lc.num_hidden_layers  # causal: 4*S^2*H*D/2
+        vit_flops = F * 936e9
+        peaks = read_peaks()
+        line = {
+            "metric": "LongVILA-8B %d-frame sequence-parallel prefill tokens/sec (vision + SP prefill + first token)" % F,
+            "value": round(S / (ms / 1e3), 1), "unit": "tok/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(ms, 2), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "LongVILA-8B %d frames x 448^2, S=%d tokens, zigzag SP-%d prefill "
+                                   "(BASELINE.json configs[4])" % (F, S, world),
+                       "parallelism": "sp%d" % world, "padded_len": plan.padded_len, "chunk": plan.chunk},
+            "phase_ms_max_over_ranks": {"vision": round(float(t[0]), 2), "embed_allgather": round(float(t[1]), 2),
+                                        "sp_prefill": round(float(t[2]), 2)},
+            "achieved_tflops_per_gpu": round((gemm_flops + attn_flops + vit_flops) / world / (ms / 1e3) / 1e12, 1),
+            "roofline": {"bound": "tensor", "achieved": round((gemm_flops + attn_flops + vit_flops) / world / (ms / 1e3) / 1e12, 1),
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": round((gemm_flops + attn_flops + vit_flops) / world / (ms / 1e3) / 1e12 / peaks["bf16_tflops_sustained"], 4),
+                         "traffic": None, "peak_source": peaks["source"] + " (sustained)"},
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -396,6 +499,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--workload", default="request", choices=["request", "sp_prefill"])
+    ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--profile", action="store_true",
                     help="profiling aid (ncu): 1 warm-up, 8 new tokens; NOT a valid bench number")
     args = ap.parse_args()
@@ -405,6 +510,8 @@ def main():
         args.no_cpu = True
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "sp_prefill":
+        run_sp(args)
     else:
         run_ours(args)
 

@@ -28,7 +28,7 @@ for st in $STAGES; do
           --log-file gpurun_out/launches.csv python bench.py --profile --steps 1 > gpurun_out/launches.log 2>&1
       echo "== launches rc=$? lines=$(wc -l < gpurun_out/launches.csv)" ;;
     ncu)
-      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:gemv_kernel -s 60 -c 3 \
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:gemv_tma_kernel -s 60 -c 4 \
           -f -o gpurun_out/prof_gemv python bench.py --profile --steps 1 > gpurun_out/ncu_gemv.log 2>&1
       echo "== ncu gemv rc=$?"; ls -la gpurun_out/*.ncu-rep 2>/dev/null ;;
     ncu_gemm)
