@@ -23,6 +23,7 @@ SOURCES = [
     "api.cu",
     "gemm_tcgen05.cu",
     "fmha_tcgen05.cu",
+    "fmha2_tcgen05.cu",
     "norm.cu",
     "data_movement.cu",
     "decode.cu",

@@ -14,6 +14,7 @@
 // Replaces flash_attn_func in SiglipFlashAttention2 (modeling_siglip.py:583-585, non-causal,
 // scale 72^-0.5) and HF _flash_attention_forward for Qwen2 (modeling_qwen2.py:191-310; causal GQA).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -380,6 +381,18 @@ int fmha_prefill(const FmhaParams& p, cudaStream_t stream) {
                p.kv_head_stride % 8 == 0 && p.o_tok_stride % 8 == 0 && p.o_head_stride % 8 == 0,
            "fmha: strides must be multiples of 8 elements (16 bytes)");
   VB_CHECK(!p.causal || p.Sk >= p.Sq, "fmha: causal needs Sk >= Sq");
+  {
+    // v2 (two query tiles per CTA, ping-pong softmax warpgroups) whenever there are >= 2 tiles
+    static int force_v1 = -1;
+    if (force_v1 < 0) {
+      const char* e = getenv("VILA_B200_FMHA_V1");
+      force_v1 = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!force_v1 && p.Sq > 128) {
+      const int rc = fmha_prefill_v2(p, stream);
+      if (rc >= 0) return rc;
+    }
+  }
   if (p.D == 128) return launch_fmha<128, 64>(p, stream);
   if (p.D <= 96 && p.D > 64) return launch_fmha<96, 32>(p, stream);
   if (p.D == 64) return launch_fmha<64, 64>(p, stream);

@@ -51,6 +51,7 @@ struct FmhaParams {
   float scale;      // softmax scale (1/sqrt(D))
 };
 int fmha_prefill(const FmhaParams& p, cudaStream_t stream);
+int fmha_prefill_v2(const FmhaParams& p, cudaStream_t stream);  // -1: shape not handled
 
 // ---- norms ---------------------------------------------------------------------------------------
 int layernorm_bf16(const __nv_bfloat16* x, const __nv_bfloat16* w, const __nv_bfloat16* b,
