@@ -22,6 +22,7 @@ SOURCES = [
     "host.cu",
     "api.cu",
     "gemm_tcgen05.cu",
+    "gemm_skinny_tcgen05.cu",
     "fmha_tcgen05.cu",
     "fmha2_tcgen05.cu",
     "norm.cu",

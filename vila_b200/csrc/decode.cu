@@ -270,6 +270,29 @@ decode_attn_kernel(DecodeAttnParams p) {
   const int pos = *p.position;       // index of the new token == number of cached tokens
   const int n_tok = pos + 1;
 
+  // ---- this split's token range; the first batch of K/V rows is requested BEFORE the RoPE
+  // prologue so that its HBM latency overlaps the prologue (K/V do not depend on q) ----
+  constexpr int TB = 4;  // tokens per half-warp per batch
+  const int per = (n_tok + p.num_splits - 1) / p.num_splits;
+  const int t0 = split * per, t1 = min(n_tok, t0 + per);
+  const int hw = warp * 2 + sub;
+  uint4 kreg[TB], vreg[TB];
+  auto load_batch = [&](int base) {
+#pragma unroll
+    for (int i = 0; i < TB; ++i) {
+      const int t = base + hw + 16 * i;
+      kreg[i] = make_uint4(0, 0, 0, 0);
+      vreg[i] = make_uint4(0, 0, 0, 0);
+      if (t < t1 && t != pos) {
+        const int page = p.page_table[t >> 7];
+        const size_t o = ((static_cast<size_t>(page) * 128 + (t & 127)) * p.Hkv + hk) * D + dl * VPT;
+        kreg[i] = ldg_v4(p.k_pool + o);
+        vreg[i] = ldg_v4(p.v_pool + o);
+      }
+    }
+  };
+  load_batch(t0);
+
   __shared__ float q_s[G][D];
   __shared__ __align__(16) __nv_bfloat16 knew_s[D];
   __shared__ __align__(16) __nv_bfloat16 vnew_s[D];
@@ -313,10 +336,6 @@ decode_attn_kernel(DecodeAttnParams p) {
     }
   }
 
-  // ---- this split's token range ----
-  const int per = (n_tok + p.num_splits - 1) / p.num_splits;
-  const int t0 = split * per, t1 = min(n_tok, t0 + per);
-
   float qreg[G][VPT];
 #pragma unroll
   for (int g = 0; g < G; ++g)
@@ -333,49 +352,47 @@ decode_attn_kernel(DecodeAttnParams p) {
   }
   const float sl2 = p.scale * 1.4426950408889634f;
 
-  for (int tb = t0 + warp * 2; tb < t1; tb += kDaWarps * 2) {  // warp-uniform trip count
-    const int t = tb + sub;
-    const bool valid = t < t1;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-    if (!valid) {
-    } else if (t == pos) {
-      kv = *reinterpret_cast<const uint4*>(knew_s + dl * VPT);
-      vv = *reinterpret_cast<const uint4*>(vnew_s + dl * VPT);
-    } else {
-      const int page = p.page_table[t >> 7];
-      const size_t o = ((static_cast<size_t>(page) * 128 + (t & 127)) * p.Hkv + hk) * D + dl * VPT;
-      kv = ldg_v4(p.k_pool + o);
-      vv = ldg_v4(p.v_pool + o);
-    }
-    const float kf[VPT] = {bf_lo(kv.x), bf_hi(kv.x), bf_lo(kv.y), bf_hi(kv.y),
-                           bf_lo(kv.z), bf_hi(kv.z), bf_lo(kv.w), bf_hi(kv.w)};
-    const float vf[VPT] = {bf_lo(vv.x), bf_hi(vv.x), bf_lo(vv.y), bf_hi(vv.y),
-                           bf_lo(vv.z), bf_hi(vv.z), bf_lo(vv.w), bf_hi(vv.w)};
+  for (int base = t0; base < t1; base += 16 * TB) {  // block-uniform trip count
+    if (base != t0) load_batch(base);
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float s = 0.f;
+    for (int i = 0; i < TB; ++i) {
+      const int t = base + hw + 16 * i;
+      const bool valid = t < t1;
+      uint4 kv = kreg[i], vv = vreg[i];
+      if (valid && t == pos) {
+        kv = *reinterpret_cast<const uint4*>(knew_s + dl * VPT);
+        vv = *reinterpret_cast<const uint4*>(vnew_s + dl * VPT);
+      }
+      const float kf[VPT] = {bf_lo(kv.x), bf_hi(kv.x), bf_lo(kv.y), bf_hi(kv.y),
+                             bf_lo(kv.z), bf_hi(kv.z), bf_lo(kv.w), bf_hi(kv.w)};
+      const float vf[VPT] = {bf_lo(vv.x), bf_hi(vv.x), bf_lo(vv.y), bf_hi(vv.y),
+                             bf_lo(vv.z), bf_hi(vv.z), bf_lo(vv.w), bf_hi(vv.w)};
 #pragma unroll
-      for (int e = 0; e < VPT; ++e) s = fmaf(qreg[g][e], kf[e], s);
-      // reduce over the 16 lanes of this half-warp
+      for (int g = 0; g < G; ++g) {
+        float s = 0.f;
 #pragma unroll
-      for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (valid) {
-        s *= sl2;
-        const float m_new = fmaxf(m[g], s);
-        const float alpha = exp2f(m[g] - m_new);  // m == -inf -> 0
-        const float pexp = exp2f(s - m_new);
-        l[g] = l[g] * alpha + pexp;
-        // the reference's attention kernels cast probabilities to bf16 before P.V
-        const float pb = bf16_round(pexp);
+        for (int e = 0; e < VPT; ++e) s = fmaf(qreg[g][e], kf[e], s);
+        // reduce over the 16 lanes of this half-warp
 #pragma unroll
-        for (int e = 0; e < VPT; ++e) o_acc[g][e] = o_acc[g][e] * alpha + pb * vf[e];
-        m[g] = m_new;
+        for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (valid) {
+          s *= sl2;
+          const float m_new = fmaxf(m[g], s);
+          const float alpha = exp2f(m[g] - m_new);  // m == -inf -> 0
+          const float pexp = exp2f(s - m_new);
+          l[g] = l[g] * alpha + pexp;
+          // the reference's attention kernels cast probabilities to bf16 before P.V
+          const float pb = bf16_round(pexp);
+#pragma unroll
+          for (int e = 0; e < VPT; ++e) o_acc[g][e] = o_acc[g][e] * alpha + pb * vf[e];
+          m[g] = m_new;
+        }
       }
     }
   }
 
   // ---- block combine: 16 half-warp partials per head ----
-  const int slot = warp * 2 + sub;
+  const int slot = hw;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     if (dl == 0) {

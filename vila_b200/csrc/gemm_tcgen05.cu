@@ -496,6 +496,11 @@ int check_args(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw,
 
 }  // namespace
 
+void get_workspace(void** ptr, size_t* bytes) {
+  *ptr = g_ws.ptr;
+  *bytes = g_ws.bytes;
+}
+
 int set_workspace(void* ptr, size_t bytes) {
   VB_CHECK(ptr == nullptr || bytes >= kCounterBytes + 1024, "workspace too small (%zu bytes)", bytes);
   VB_CHECK((reinterpret_cast<uintptr_t>(ptr) & 255) == 0, "workspace must be 256-byte aligned");
@@ -526,6 +531,11 @@ int gemm_bf16_cfg(int block_n, const __nv_bfloat16* A, int lda, const __nv_bfloa
                   __nv_bfloat16* C, int ldc, int M, int N, int K, const GemmEpilogue& epi,
                   cudaStream_t stream) {
   if (check_args(A, lda, W, ldw, C, ldc, M, N, K, epi)) return 1;
+  if (block_n == 3000) {
+    const int rc = gemm_skinny_bf16(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
+    if (rc < 0) set_last_error("gemm_bf16_cfg: skinny kernel does not handle M=%d", M);
+    return rc < 0 ? 1 : rc;
+  }
   int fsk = -1;
   if (block_n >= 2000) {
     fsk = 0;
