@@ -10,7 +10,8 @@
 //   has its next S tile being computed while it accumulates O, and the tensor pipe alternates tiles.
 //
 // Same math / rounding as v1 (fmha_tcgen05.cu): S = QK^T in fp32, online softmax in fp32 with exp2,
-// P cast to bf16 for the PV MMA, O rescaled and accumulated in fp32 registers, d=72 zero-padded to 96
+// P cast to bf16 for the PV MMA, O accumulated in TMEM by the PV MMA itself with a lazy (exact)
+// rescale when a row maximum moves by more than 2^8, d=72 zero-padded to 96
 // by TMA OOB fill (SW64 chunks), d=128 as two SW128 chunks, V consumed as the MN-major B operand.
 #include <math.h>
 
@@ -184,8 +185,7 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         umma_commit(&s_full[t]);
       };
       auto issue_pv = [&](int t, int j) {  // O_t(j) = P_t(j) V(j)
-        mbar_wait(&p_full[t], j & 1);
-        mbar_wait(&o_free[t], (j & 1) ^ 1);
+        mbar_wait(&p_full[t], j & 1);  // also orders this PV after any O rescale of block j
         tc_fence_after();
         const uint8_t* vs = ring_s + ((2 * j + 1) % R) * C::kTileBytes;
 #pragma unroll
@@ -194,7 +194,7 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               smem_u32(p_s + t * C::kPBytes + (k >> 2) * (BQ * 128)) + (k & 3) * 32, 16, 1024, kLayoutSW128);
           const uint64_t bd = make_smem_desc(smem_u32(vs) + k * 16 * (CW * 2), C::kChunkBytes, C::kSBO,
                                              C::kLayout);
-          umma_f16(tmem_base + 256 + t * 128, ad, bd, idesc_o, k != 0 ? 1u : 0u);
+          umma_f16(tmem_base + 256 + t * 128, ad, bd, idesc_o, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit(&p_free[t]);
         umma_commit(&o_full[t]);
@@ -237,10 +237,13 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int n = nblk[t];
     uint8_t* my_p = p_s + t * C::kPBytes;
-    float m = -INFINITY, l = 0.f;
-    float o_acc[DP];
-#pragma unroll
-    for (int i = 0; i < DP; ++i) o_acc[i] = 0.f;
+    // O accumulates in TMEM across KV blocks (the PV MMA runs with accumulate=1).  Each row keeps a
+    // reference maximum m_ref; the accumulator is rescaled (tcgen05.ld -> scale -> tcgen05.st) only
+    // when a row's running maximum exceeds m_ref by more than 2^8 (exact: P, l and O all use the same
+    // m_ref, the final division by l cancels it).  The decision is per warp (TMEM ld/st are
+    // warp-collective on the warp's own 32 lanes).
+    float m_ref = -INFINITY, l = 0.f;
+    const uint32_t o_addr = tmem_base + lane_addr + 256 + t * 128;
 
     for (int j = 0; j < n; ++j) {
       mbar_wait(&s_full[t], j & 1);
@@ -265,9 +268,30 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
       }
-      const float m_new = fmaxf(m, mx * a.scale_log2);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2f(m - m_use);
+      const float m_blk = mx * a.scale_log2;
+      if (j == 0) {
+        m_ref = (m_blk == -INFINITY) ? 0.f : m_blk;
+      } else {
+        const bool need = m_blk > m_ref + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? m_blk : m_ref;
+          const float alpha = ex2f(m_ref - m_new);  // 1 for rows that keep their reference
+          mbar_wait(&o_full[t], (j - 1) & 1);       // PV(j-1) has landed in TMEM
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < DP / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(o_addr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_32x32b_x32(o_addr + c * 32, r);
+          }
+          tmem_st_wait();
+          l *= alpha;
+          m_ref = m_new;
+        }
+      }
 
       mbar_wait(&p_free[t], (j & 1) ^ 1);
       float rowsum = 0.f;
@@ -279,7 +303,7 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         float p[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float e = ex2f(__uint_as_float(r[i]) * a.scale_log2 - m_use);
+          float e = ex2f(__uint_as_float(r[i]) * a.scale_log2 - m_ref);
           if (need_mask) e = (kv0 + c * 32 + i <= kv_lim) ? e : 0.f;
           p[i] = e;
           rowsum += e;
@@ -296,42 +320,36 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           *reinterpret_cast<uint4*>(prow + ((piece ^ (row & 7)) << 4)) = v4;
         }
       }
-      l = l * alpha + rowsum;
-      m = m_new;
+      l += rowsum;
       fence_proxy_async_smem();
-      mbar_arrive(&p_full[t]);
       tc_fence_before();
+      mbar_arrive(&p_full[t]);
       mbar_arrive(&s_free[t]);
+    }
 
-      mbar_wait(&o_full[t], j & 1);
+    if (n > 0) {
+      mbar_wait(&o_full[t], (n - 1) & 1);
       tc_fence_after();
-      const uint32_t o_addr = tmem_base + lane_addr + 256 + t * 128;
-#pragma unroll
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      __nv_bfloat16* dst = a.o + static_cast<int64_t>(b * a.Sq + q_idx) * a.o_tok_stride +
+                           static_cast<int64_t>(h) * a.o_head_stride;
+#pragma unroll 1
       for (int c = 0; c < DP / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(o_addr + c * 32, r);
         tmem_ld_wait();
+        if (q_idx < a.Sq) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(r[i]);
-      }
-      tc_fence_before();
-      mbar_arrive(&o_free[t]);
-    }
-
-    if (n > 0 && q_idx < a.Sq) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      __nv_bfloat16* dst = a.o + static_cast<int64_t>(b * a.Sq + q_idx) * a.o_tok_stride +
-                           static_cast<int64_t>(h) * a.o_head_stride;
-#pragma unroll
-      for (int g = 0; g < DP / 8; ++g) {
-        if (g * 8 < a.D) {
-          uint4 v4;
-          v4.x = pack_bf16(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
-          v4.y = pack_bf16(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
-          v4.z = pack_bf16(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
-          v4.w = pack_bf16(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
-          stg_v4(dst + g * 8, v4);
+          for (int g = 0; g < 4; ++g) {
+            if (c * 32 + g * 8 < a.D) {
+              uint4 v4;
+              v4.x = pack_bf16(__uint_as_float(r[g * 8 + 0]) * inv, __uint_as_float(r[g * 8 + 1]) * inv);
+              v4.y = pack_bf16(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv);
+              v4.z = pack_bf16(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv);
+              v4.w = pack_bf16(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv);
+              stg_v4(dst + c * 32 + g * 8, v4);
+            }
+          }
         }
       }
     }
