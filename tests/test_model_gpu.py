@@ -79,8 +79,11 @@ def test_encode_images_dynamic_s2(cuda, idx):
         check_close(f"dynamic_s2 image {i}", a, b, c)
 
 
-def test_generate_greedy_matches_oracle(cuda):
+@pytest.mark.parametrize("decoder", ["mega", "graph"])
+def test_generate_greedy_matches_oracle(cuda, decoder, monkeypatch):
+    """decoder: persistent mega-kernel (default) or the CUDA graph of per-layer kernels"""
     from vila_b200.model import tiny_test_config
+    monkeypatch.setenv("VILA_B200_DECODER", decoder)
     cfg = tiny_test_config(llm_layers=3)
     model = build(cfg, seed=6)
     ids, images = synth_inputs(cfg, n_images=1, n_text=12)

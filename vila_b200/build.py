@@ -29,6 +29,7 @@ SOURCES = [
     "data_movement.cu",
     "decode.cu",
     "gemv_tma.cu",
+    "decode_mega.cu",
 ]
 HEADERS = ["common.cuh", "kernels.h", "../../include/vila_b200.h"]
 

@@ -202,4 +202,26 @@ int vila_decode_attention(const vila_decode_attn_params* p, void* stream) {
   return vb::decode_attention(d, st(stream));
 }
 
+int vila_decode_mega(const vila_mega_params* p, void* stream) {
+  VB_REQUIRE_DEVICE();
+  static_assert(sizeof(vila_mega_layer) == sizeof(vb::MegaLayer), "layer struct mismatch");
+  vb::MegaParams m;
+  m.layers = reinterpret_cast<const vb::MegaLayer*>(p->layers);
+  m.num_layers = p->num_layers;
+  m.final_norm_w = cb(p->final_norm_w);
+  m.lm_head_w = cb(p->lm_head_w);
+  m.embed = cb(p->embed);
+  m.hidden = p->hidden; m.inter = p->inter; m.Hq = p->Hq; m.Hkv = p->Hkv; m.vocab = p->vocab;
+  m.eps = p->eps; m.scale = p->scale;
+  m.inv_freq = p->inv_freq;
+  m.page_table = p->page_table;
+  m.x = mb(p->x); m.qkv = mb(p->qkv); m.act = mb(p->act);
+  m.attn_ws = p->attn_ws;
+  m.key = p->key; m.token = p->token; m.hist = p->hist; m.step = p->step; m.position = p->position;
+  m.barrier = p->barrier; m.epoch = p->epoch;
+  m.n_tokens = p->n_tokens; m.splits = p->splits;
+  m.ks_hidden = m.ks_inter = m.ks_attn = m.xs_bytes = 0;
+  return vb::decode_mega(m, st(stream));
+}
+
 }  // extern "C"

@@ -4,7 +4,7 @@ from .configuration import (LlavaConfig, Qwen2Config, SiglipVisionConfig, nvila_
 from .llava_llama import (BasicImageEncoder, BasicVideoEncoder, LlavaLlamaModel, SyntheticTokenizer,
                           TSPVideoEncoder)
 from .projector import MultimodalProjector
-from .qwen2 import GraphDecoder, PagedKVCache, Qwen2ForCausalLM
+from .qwen2 import GraphDecoder, MegaDecoder, PagedKVCache, Qwen2ForCausalLM
 from .vision import SiglipVisionModel, SiglipVisionTower
 
 __all__ = [n for n in dir() if not n.startswith("_")]
