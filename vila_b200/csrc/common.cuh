@@ -29,6 +29,7 @@ void set_last_error(const char* fmt, ...);
     if (_e != cudaSuccess) {                                                            \
       ::vb::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
                            __FILE__, __LINE__);                                         \
+      (void)cudaGetLastError(); /* do not leave a stale error for the caller's runtime */ \
       return 2;                                                                         \
     }                                                                                   \
   } while (0)

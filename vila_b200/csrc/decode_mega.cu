@@ -552,13 +552,13 @@ int decode_mega(const MegaParams& pin, cudaStream_t stream) {
   need_acc = max(need_acc, rows((p.Hq + 2 * p.Hkv) * MD, p.ks_hidden, false));
   VB_CHECK(need_acc <= ACC_FLOATS, "decode_mega: %d accumulator slots needed (max %d)", need_acc, ACC_FLOATS);
   const size_t smem = static_cast<size_t>(xs_bytes) + ACC_FLOATS * 4 + MW * MSTAGES * SLOT + MW * MSTAGES * 8 + 128;
-  VB_CHECK(smem <= 227 * 1024, "decode_mega: needs %zu bytes of shared memory", smem);
+  VB_CHECK(smem <= 225 * 1024, "decode_mega: needs %zu bytes of shared memory", smem);
 #define VB_MEGA_CASE(GG)                                                                         \
   case GG: {                                                                                     \
     auto kern = decode_mega_kernel<GG>;                                                          \
     static bool attr_done = false;                                                               \
     if (!attr_done) {                                                                            \
-      VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); \
       attr_done = true;                                                                          \
     }                                                                                            \
     int occ = 0;                                                                                 \
