@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(MegaParams p) {
   float* acc = reinterpret_cast<float*>(smem + p.xs_bytes);
   uint8_t* ring = smem + p.xs_bytes + ACC_FLOATS * 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + MW * MSTAGES * SLOT);
+  MegaLayer* layers_s = reinterpret_cast<MegaLayer*>(bars + MW * MSTAGES);  // [num_layers] copy
   __shared__ float red[32];
   __shared__ unsigned long long best_s;
 
@@ -130,7 +131,13 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(MegaParams p) {
     for (int s = 0; s < MSTAGES; ++s) mbar_init(&my_bars[s], 1);
     fence_barrier_init();
   }
-  __syncwarp();
+  {  // the per-layer pointer table is read on every chunk issue: keep it in shared memory
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(p.layers);
+    uint64_t* dst = reinterpret_cast<uint64_t*>(layers_s);
+    for (int i = threadIdx.x; i < p.num_layers * static_cast<int>(sizeof(MegaLayer) / 8); i += MT) dst[i] = src[i];
+  }
+  __syncthreads();
+  p.layers = layers_s;
 
   unsigned int sync_target = *reinterpret_cast<volatile unsigned int*>(p.epoch);
 
@@ -142,22 +149,33 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(MegaParams p) {
     const int items = nrows > 0 ? nrows * ph.ks : 0;
     return items > warp ? (items - warp + MW - 1) / MW : 0;
   };
+  // cached description of the producer's current phase (refreshed only when pg changes)
+  int pg_in_tok = 0, p_nmy = 0, p_ks = 1, p_ce = 0, p_K = 0;
+  const __nv_bfloat16* p_wbase = nullptr;  // first row of this CTA's slab
+  auto producer_load_phase = [&]() {
+    const GPhase ph = get_phase(p, pg_in_tok);
+    p_nmy = my_items(ph);
+    p_ks = ph.ks;
+    p_K = ph.K;
+    p_ce = ph.K / ph.ks;
+    p_wbase = ph.w + static_cast<size_t>(cta) * ph.rpb * ph.K;
+  };
+  producer_load_phase();
   auto producer_advance = [&]() {  // lane 0 only
     while (issued - consumed < MSTAGES && pg < total_gphases) {
-      const GPhase ph = get_phase(p, pg % gphases_per_token);
-      const int n_my = my_items(ph);
-      if (pj >= n_my) {
+      if (pj >= p_nmy) {
         ++pg;
         pj = 0;
+        if (++pg_in_tok == gphases_per_token) pg_in_tok = 0;
+        if (pg < total_gphases) producer_load_phase();
         continue;
       }
       const int item = warp + pj * MW;
-      const int r = item / ph.ks, part = item - r * ph.ks;
-      const int ce = ph.K / ph.ks;
-      const __nv_bfloat16* src = ph.w + static_cast<size_t>(cta * ph.rpb + r) * ph.K + part * ce;
+      const int r = item / p_ks, part = item - r * p_ks;
+      const __nv_bfloat16* src = p_wbase + static_cast<size_t>(r) * p_K + part * p_ce;
       const int s = issued % MSTAGES;
-      mbar_arrive_expect_tx(&my_bars[s], ce * 2);
-      bulk_g2s(my_ring + s * SLOT, src, ce * 2, &my_bars[s]);
+      mbar_arrive_expect_tx(&my_bars[s], p_ce * 2);
+      bulk_g2s(my_ring + s * SLOT, src, p_ce * 2, &my_bars[s]);
       ++issued;
       ++pj;
     }
@@ -551,7 +569,9 @@ int decode_mega(const MegaParams& pin, cudaStream_t stream) {
   need_acc = max(need_acc, rows(p.hidden, p.ks_attn, false));
   need_acc = max(need_acc, rows((p.Hq + 2 * p.Hkv) * MD, p.ks_hidden, false));
   VB_CHECK(need_acc <= ACC_FLOATS, "decode_mega: %d accumulator slots needed (max %d)", need_acc, ACC_FLOATS);
-  const size_t smem = static_cast<size_t>(xs_bytes) + ACC_FLOATS * 4 + MW * MSTAGES * SLOT + MW * MSTAGES * 8 + 128;
+  VB_CHECK(p.num_layers <= 64, "decode_mega: at most 64 layers");
+  const size_t smem = static_cast<size_t>(xs_bytes) + ACC_FLOATS * 4 + MW * MSTAGES * SLOT + MW * MSTAGES * 8 +
+                      static_cast<size_t>(p.num_layers) * sizeof(MegaLayer) + 128;
   VB_CHECK(smem <= 225 * 1024, "decode_mega: needs %zu bytes of shared memory", smem);
 #define VB_MEGA_CASE(GG)                                                                         \
   case GG: {                                                                                     \
