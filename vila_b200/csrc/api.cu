@@ -1,6 +1,9 @@
 // extern "C" surface declared in include/vila_b200.h: thin argument marshalling onto vb::*.
 #include "../../include/vila_b200.h"
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -221,6 +224,18 @@ int vila_decode_mega(const vila_mega_params* p, void* stream) {
   m.barrier = p->barrier; m.epoch = p->epoch;
   m.n_tokens = p->n_tokens; m.splits = p->splits;
   m.ks_hidden = m.ks_inter = m.ks_attn = m.xs_bytes = 0;
+  {
+    // profiling aid: VILA_B200_MEGA_DEBUG=<device pointer in hex>,<cta>
+    const char* e = getenv("VILA_B200_MEGA_DEBUG");
+    if (e != nullptr) {
+      unsigned long long ptr = 0;
+      int cta = 0;
+      if (sscanf(e, "%llx,%d", &ptr, &cta) >= 1) {
+        m.debug_times = reinterpret_cast<long long*>(ptr);
+        m.debug_cta = cta;
+      }
+    }
+  }
   return vb::decode_mega(m, st(stream));
 }
 

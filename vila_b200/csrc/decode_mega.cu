@@ -140,6 +140,11 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(MegaParams p) {
   p.layers = layers_s;
 
   unsigned int sync_target = *reinterpret_cast<volatile unsigned int*>(p.epoch);
+  long long* dbg = p.debug_times;  // optional [n_phases][6] clock64 stamps of CTA `debug_cta`
+  int dbg_i = 0;
+  auto stamp = [&](int k) {
+    if (dbg != nullptr && cta == p.debug_cta && threadIdx.x == 0) dbg[dbg_i * 6 + k] = clock64();
+  };
 
   // ---------------- ring producer (lane 0 of every warp) ----------------
   int issued = 0, consumed = 0;    // chunks of this warp
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(MegaParams p) {
       const int nrows = max(0, min(ph.rpb, ph.N - row0));
       const int nvec = ph.K >> 3;
 
+      stamp(0);
       // ================= attention phase (before the o_proj GEMV of each layer) =================
       if (ph.kind == 1) {
         if (cta < p.Hkv * p.splits) {
@@ -354,6 +360,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(MegaParams p) {
         sync_target += grid;
         grid_sync(p.barrier, sync_target);
       }
+      stamp(1);
 
       // ================= stage the activation vector of this GEMV phase =================
       if (ph.kind == 1) {
@@ -423,6 +430,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(MegaParams p) {
       }
       if (threadIdx.x == 0) best_s = 0ull;
       __syncthreads();
+      stamp(2);
 
       // ================= consume this warp's chunks of the phase =================
       {
@@ -454,6 +462,7 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(MegaParams p) {
         }
       }
       __syncthreads();
+      stamp(3);
       if (ph.ks > 1) {
         for (int base = 0; base < nrows; base += MT) {
           const int i = base + threadIdx.x;
@@ -501,8 +510,11 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(MegaParams p) {
           out[row0 + r] = __float2bfloat16(v);
         }
       }
+      stamp(4);
       sync_target += grid;
       grid_sync(p.barrier, sync_target);
+      stamp(5);
+      ++dbg_i;
     }
 
     // ================= finalize the token =================

@@ -164,6 +164,8 @@ struct MegaParams {
   int n_tokens, splits;
   // derived by the launcher
   int ks_hidden, ks_inter, ks_attn, xs_bytes;
+  long long* debug_times = nullptr;  // optional [phases][6] clock64 stamps (profiling aid)
+  int debug_cta = 0;
 };
 int decode_mega(const MegaParams& p, cudaStream_t stream);
 
