@@ -204,6 +204,7 @@ typedef struct vila_mega_params {
   void* qkv;
   void* act;
   float* attn_ws;
+  int32_t* attn_counters; /* Hkv ints, zero before the first launch */
   unsigned long long* key;
   int32_t* token;
   int32_t* hist;

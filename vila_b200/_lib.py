@@ -53,7 +53,7 @@ class MegaParams(C.Structure):
         ("hidden", C.c_int32), ("inter", C.c_int32), ("Hq", C.c_int32), ("Hkv", C.c_int32),
         ("vocab", C.c_int32), ("eps", c_float), ("scale", c_float),
         ("inv_freq", c_void_p), ("page_table", c_void_p),
-        ("x", c_void_p), ("qkv", c_void_p), ("act", c_void_p), ("attn_ws", c_void_p),
+        ("x", c_void_p), ("qkv", c_void_p), ("act", c_void_p), ("attn_ws", c_void_p), ("attn_counters", c_void_p),
         ("key", c_void_p), ("token", c_void_p), ("hist", c_void_p), ("step", c_void_p),
         ("position", c_void_p), ("barrier", c_void_p), ("epoch", c_void_p),
         ("n_tokens", C.c_int32), ("splits", C.c_int32),

@@ -220,6 +220,7 @@ int vila_decode_mega(const vila_mega_params* p, void* stream) {
   m.page_table = p->page_table;
   m.x = mb(p->x); m.qkv = mb(p->qkv); m.act = mb(p->act);
   m.attn_ws = p->attn_ws;
+  m.attn_counters = p->attn_counters;
   m.key = p->key; m.token = p->token; m.hist = p->hist; m.step = p->step; m.position = p->position;
   m.barrier = p->barrier; m.epoch = p->epoch;
   m.n_tokens = p->n_tokens; m.splits = p->splits;

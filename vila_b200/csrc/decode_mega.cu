@@ -356,6 +356,44 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(MegaParams p) {
             }
             ws_o[b * MD + d] = oo;
           }
+          // the last-arriving split CTA of this KV head combines all splits and publishes the bf16
+          // attention vector (so the o_proj phase stages a plain 2*Hq*128-byte vector)
+          __shared__ int is_last_s;
+          __threadfence();
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            const int prev = atomicAdd(&p.attn_counters[hk], 1);
+            is_last_s = (prev == p.splits - 1);
+            if (is_last_s) p.attn_counters[hk] = 0;
+          }
+          __syncthreads();
+          if (is_last_s) {
+            __threadfence();
+            constexpr int MAXS = 16;
+            for (int idx = threadIdx.x; idx < G * MD; idx += MT) {
+              const int gq = idx / MD, d = idx % MD;
+              float ms[MAXS], ls[MAXS], os[MAXS];
+#pragma unroll
+              for (int s = 0; s < MAXS; ++s) {
+                const bool ok = s < p.splits;
+                const size_t b = (static_cast<size_t>(hk) * p.splits + (ok ? s : 0)) * G + gq;
+                ms[s] = ok ? __ldcg(ws_m + b) : -INFINITY;
+                ls[s] = ok ? __ldcg(ws_l + b) : 0.f;
+                os[s] = ok ? __ldcg(ws_o + b * MD + d) : 0.f;
+              }
+              float mm = -INFINITY;
+#pragma unroll
+              for (int s = 0; s < MAXS; ++s) mm = fmaxf(mm, ms[s]);
+              float ll = 0.f, oo = 0.f;
+#pragma unroll
+              for (int s = 0; s < MAXS; ++s) {
+                const float w = (ms[s] == -INFINITY) ? 0.f : exp2f(ms[s] - mm);
+                ll += ls[s] * w;
+                oo += os[s] * w;
+              }
+              p.act[(hk * G + gq) * MD + d] = __float2bfloat16(oo / ll);  // act doubles as the attn vector
+            }
+          }
         }
         sync_target += grid;
         grid_sync(p.barrier, sync_target);
@@ -363,30 +401,8 @@ __global__ void __launch_bounds__(MT, 1) decode_mega_kernel(MegaParams p) {
       stamp(1);
 
       // ================= stage the activation vector of this GEMV phase =================
-      if (ph.kind == 1) {
-        // attn = combine(split partials) for all heads -> bf16 vector (K = Hq*128)
-        const float* ws_m = p.attn_ws;
-        const float* ws_l = ws_m + p.Hkv * p.splits * G;
-        const float* ws_o = ws_l + p.Hkv * p.splits * G;
-        __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(xs);
-        for (int idx = threadIdx.x; idx < p.Hq * MD; idx += MT) {
-          const int hq = idx / MD, d = idx % MD;
-          const int hk = hq / G, gq = hq % G;
-          float mm = -INFINITY;
-          for (int s = 0; s < p.splits; ++s)
-            mm = fmaxf(mm, __ldcg(ws_m + (static_cast<size_t>(hk) * p.splits + s) * G + gq));
-          float ll = 0.f, oo = 0.f;
-          for (int s = 0; s < p.splits; ++s) {
-            const size_t b = (static_cast<size_t>(hk) * p.splits + s) * G + gq;
-            const float ms = __ldcg(ws_m + b);
-            const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
-            ll += __ldcg(ws_l + b) * w;
-            oo += __ldcg(ws_o + b * MD + d) * w;
-          }
-          xb[idx] = __float2bfloat16(oo / ll);
-        }
-      } else {
-        const __nv_bfloat16* xsrc = (ph.kind == 3) ? p.act : p.x;
+      {
+        const __nv_bfloat16* xsrc = (ph.kind == 3 || ph.kind == 1) ? p.act : p.x;
         const __nv_bfloat16* nw = nullptr;
         if (ph.kind == 0) nw = p.layers[layer].ln1_w;
         else if (ph.kind == 2) nw = p.layers[layer].ln2_w;
@@ -561,7 +577,8 @@ int decode_mega(const MegaParams& pin, cudaStream_t stream) {
   const int G = p.Hq / p.Hkv;
   const int sms = num_sms();
   const int grid = sms;
-  VB_CHECK(p.Hkv * p.splits <= grid, "decode_mega: Hkv*splits exceeds the grid");
+  VB_CHECK(p.Hkv * p.splits <= grid && p.splits <= 16, "decode_mega: Hkv*splits exceeds the grid / splits > 16");
+  VB_CHECK(p.inter >= p.Hq * MD, "decode_mega: act buffer (inter) must hold the attention vector");
   const int kmax = p.hidden > p.inter ? p.hidden : p.inter;
   const int attn_bytes = (G * MD * 4) + 2 * MD * 2 + 2 * MW * G * 4 + MW * G * MD * 4;
   int xs_bytes = kmax * 2;

@@ -154,6 +154,7 @@ struct MegaParams {
   __nv_bfloat16* qkv;   // [(Hq+2Hkv)*128]
   __nv_bfloat16* act;   // [inter]
   float* attn_ws;       // [Hkv*splits*G*(128+2)]
+  int* attn_counters;   // [Hkv] zero-initialised (self-cleaning)
   unsigned long long* key;
   int32_t* token;
   int32_t* hist;

@@ -506,6 +506,7 @@ class MegaDecoder(GraphDecoder):
         p.page_table = self.cache.page_table.data_ptr()
         p.x, p.qkv, p.act = self.x.data_ptr(), self.qkv.data_ptr(), self.act.data_ptr()
         p.attn_ws = self.attn_ws.data_ptr()
+        p.attn_counters = self.counters.data_ptr()
         p.key, p.token, p.hist = self.key.data_ptr(), self.token.data_ptr(), self.hist.data_ptr()
         p.step, p.position = self.step.data_ptr(), self.position.data_ptr()
         p.barrier, p.epoch = self.barrier.data_ptr(), self.epoch.data_ptr()
