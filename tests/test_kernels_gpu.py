@@ -43,9 +43,9 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("block_n", [None, 64, 128, 256, 1064, 1128, 1256, 3000])  # 1000+: stream-K, 3000: skinny
+@pytest.mark.parametrize("block_n", [None, 64, 128, 256, 1064, 1128, 1256, 3000, 3001, 4128, 4256])  # 1000+: stream-K, 3000/3001: skinny single / CTA pair, 4xxx: CTA-pair tiles
 def test_linear_plain(cuda, M, N, K, block_n):
-    if block_n == 3000 and M > 512:
+    if block_n in (3000, 3001) and M > 512:
         pytest.skip("skinny kernel handles M <= 512")
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
@@ -89,7 +89,7 @@ def test_linear_streamk_epilogues_and_workspace_is_clean(cuda):
         w = bf(torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K))
         b = bf(torch.randn(N, device=cuda, generator=g))
         res = bf(torch.randn(M, N, device=cuda, generator=g))
-        for bn in (1064, 1128, 1256) + ((3000,) if M <= 512 else ()):
+        for bn in (1064, 1128, 1256, 4128, 4256) + ((3000, 3001) if M <= 512 else ()):
             out = ops.linear(x, w, b, act=1, residual=res, block_n=bn, static_w=True)
             assert torch.equal(out, ops.linear(x, w, b, act=1, residual=res, block_n=bn, static_w=True))
             ref = rb(rb(O.gelu_tanh(rb(x.float() @ w.float().t() + b.float()))) + res.float())

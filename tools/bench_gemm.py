@@ -13,7 +13,13 @@ shapes = {
     "vit_fc2": (1024, 1152, 4304), "llm_qkv": (279, 4608, 3584), "llm_o": (279, 3584, 3584),
     "llm_gu": (279, 37888, 3584), "llm_down": (279, 3584, 18944), "proj1": (256, 3584, 4608),
     "big": (8192, 8192, 8192),
+    # mid-size: batched ViT (16 tiles) and long-context LLM prefill
+    "mid_vit16_qkv": (16384, 3456, 1152), "mid_vit16_fc2": (16384, 1152, 4304),
+    "mid_vit4_fc1": (4096, 4304, 1152), "mid_llm2k_o": (2048, 3584, 3584),
+    "mid_llm2k_gu": (2048, 37888, 3584), "mid_llm1k_down": (1280, 3584, 18944),
 }
+if len(sys.argv) > 1:  # optional name filter, e.g. "llm"
+    shapes = {k: v for k, v in shapes.items() if any(a in k for a in sys.argv[1:])}
 res = {}
 def timeit(fn, reps=20):
     for _ in range(3): fn()
@@ -34,7 +40,7 @@ for name, (M, N, K) in shapes.items():
         return ws[idx[0]]
     us = timeit(lambda: torch.matmul(x, nxt().t(), out=out), reps=5 if name == "big" else 20)
     row = {"cublas_us": round(us, 2), "cublas_tflops": round(2 * M * N * K / us / 1e6, 1)}
-    for cfg in (None, 2128, 2256) + ((3000,) if M <= 512 else ()):
+    for cfg in (None, 2128, 2256, 4128, 4256) + ((3000, 3001) if M <= 512 else ()):
         try:
             us = timeit(lambda: ops.linear(x, nxt(), out=out, block_n=cfg, static_w=True), reps=5 if name == "big" else 20)
             row[str(cfg)] = round(us, 2)

@@ -1,28 +1,45 @@
 // Skinny-M ("swap-AB") bf16 GEMM for sm_100a:  C[M,N] = epi(X[M,K] · W[N,K]^T),  M <= 512 tokens.
 //
 // At prefill of a short prompt (M ~ 280) or a small decode batch the weights dominate the traffic and
-// a 128-row token tile wastes the tensor core (280 rows -> 3 tiles = 384 rows) while leaving SMs idle
-// (N/128 x 3 tiles).  Here the roles are swapped: the UMMA M dimension (128 TMEM lanes) carries 128
-// WEIGHT rows and the UMMA N dimension carries ALL tokens (padded only to a multiple of 32, issued as
-// 256-wide + remainder instructions), so every weight byte is fetched exactly once, and the K
-// dimension is split across CTAs so that (N/128) x splits ~ 148 units fill the machine.  Partial sums
-// of the splits are parked in fp32 workspace slots and added in a fixed order by the last-arriving
-// CTA (deterministic).
+// a 128-row token tile wastes the tensor core (280 rows -> 3 tiles = 384 rows), re-reads the weight
+// tile once per token tile through the ~50 B/clk L2->SM port, and leaves SMs idle.  Here the roles
+// are swapped: the UMMA M dimension (TMEM lanes) carries WEIGHT rows and the UMMA N dimension carries
+// ALL tokens (padded only to a multiple of 32, issued as one or two equal UMMA N chunks), so every
+// weight byte enters an SM exactly once, and the K dimension is split across CTAs so that the machine
+// is filled.  Partial sums of the splits are parked in fp32 workspace slots and added in a fixed
+// order by the last-arriving CTA (deterministic).
 //
-//   warp 0: TMA producer (W tile 128x64 + token tile M_pad x 64 per k-block, 128B swizzle)
-//   warp 1: tcgen05.mma issuer + TMEM allocator (accumulator: 128 lanes x M_pad fp32 columns)
-//   warps 2-5: epilogue — lane == output feature n, column == token m: C[m, n] written as 64-byte
-//              coalesced segments per token; bias / GELU / residual / SwiGLU as in gemm_tcgen05.cu
+// Two flavours of the same kernel:
+//   kPair = false : one CTA = 128 weight rows, tcgen05.mma.cta_group::1, loads the whole token tile
+//   kPair = true  : a 2-CTA cluster = 256 weight rows, ONE tcgen05.mma.cta_group::2 (M = 256) issued
+//                   by the leader CTA; each CTA stages its own 128 weight rows plus HALF of the token
+//                   tile (the tensor cores of both SMs read both halves), which halves the token
+//                   bytes per SM — the term that bounds the single-CTA flavour.  Both CTAs' TMA loads
+//                   signal the leader's "full" barrier; the leader's tcgen05.commit multicasts the
+//                   "stage free" / "accumulator ready" arrivals to both CTAs.
+//
+//   warp 0: TMA producer (W tile 128x64 + token rows x 64 per k-block, 128B swizzle)
+//   warp 1: tcgen05.mma issuer (leader CTA only in pair mode) + TMEM allocator
+//           (accumulator: 128 lanes x M_pad fp32 columns per CTA)
+//   warps 2-5: epilogue — TMEM lane == output feature n, column == token m.  32-token chunks are
+//              transposed through a double-buffered shared-memory staging tile so that C[m, n0..]
+//              leaves the SM as 16-byte vectors in 256-byte rows; bias / GELU / residual / SwiGLU
+//              with the rounding points of gemm_tcgen05.cu.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vb {
 namespace {
 
-constexpr int BW = 128;      // weight rows per tile (UMMA M)
+constexpr int BW = 128;      // weight rows per CTA (TMEM lanes)
 constexpr int BK = 64;
 constexpr int kThreads = 192;
 constexpr size_t kCounterBytes = 64 * 1024;
+constexpr int kStgPitch = BW * 2 + 16;           // staging row (one token, 128 features) + pad
+constexpr int kStgBytes = 2 * 32 * kStgPitch;    // double buffer of 32 tokens
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
@@ -39,23 +56,33 @@ struct SkinnyArgs {
   __nv_bfloat16* C;
   int ldc, M, N, K;
   int m_pad;        // tokens padded to a multiple of 32 (<= 512)
+  int chunk;        // tokens per UMMA instruction: m_pad (<= 256) or m_pad / 2
   int stages;
-  int splits;       // k-splits per weight block
+  int splits;       // k-splits per weight block (pair mode: per pair of weight blocks)
   int kb_per_split;
-  float* ws;        // [unit][m_pad][128] fp32 partials
+  float* ws;        // [n_blk][split][m_pad][128] fp32 partials
   int* counters;    // [n_blocks]
   GemmEpilogue epi;
+  long long* dbg;   // profiling aid (VILA_B200_GEMM_DEBUG): 8 counters per CTA, or nullptr
 };
 
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                    SkinnyArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  const int x_bytes = a.m_pad * BK * 2;
-  const int stage_bytes = BW * BK * 2 + x_bytes;
-  uint8_t* bar_base = smem + a.stages * stage_bytes;
+  const int x_rows = kPair ? a.m_pad / 2 : a.m_pad;  // token rows staged by THIS CTA per k-block
+  const int stage_bytes = BW * BK * 2 + x_rows * BK * 2;
+  uint8_t* stg = smem + a.stages * stage_bytes;
+  uint8_t* bar_base = stg + kStgBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* acc_full = empty_bar + 8;
@@ -63,8 +90,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   uint32_t* last_flag = tmem_ptr + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x;
-  const int n_blk = unit / a.splits, split = unit - n_blk * a.splits;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int unit = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int nb = unit / a.splits, split = unit - nb * a.splits;
+  const int n_blk = kPair ? nb * 2 + static_cast<int>(rank) : nb;
   const int nkb = (a.K + BK - 1) / BK;
   const int kb0 = split * a.kb_per_split;
   const int kb1 = min(nkb, kb0 + a.kb_per_split);
@@ -79,20 +108,43 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  if (warp == 1) {
+    if (kPair) tmem_alloc_pair<512>(tmem_ptr);
+    else tmem_alloc<512>(tmem_ptr);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();  // peer barriers are initialised before any remote signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   griddep_launch_dependents();
 
+  long long* dbg = a.dbg ? a.dbg + 8 * blockIdx.x : nullptr;
+  long long e0 = 0, e1 = 0;
+  if (dbg && threadIdx.x == 0) {
+    dbg[0] = gtime_ns();
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    dbg[6] = smid;
+  }
   if (warp == 0) {
     if (lane == 0) {
+      long long w_empty = 0;
+      // every load of the pair reports to the LEADER's full barrier
+      auto full_addr = [&](int i) {
+        const uint32_t own = smem_u32(&full_bar[i]);
+        return kPair ? mapa_u32(own, 0) : own;
+      };
+      auto load = [&](void* dst, const CUtensorMap* tm, int i, int c0, int c1) {
+        if (kPair) tma_load_2d_pair(dst, tm, full_addr(i), c0, c1);
+        else tma_load_2d(dst, tm, &full_bar[i], c0, c1);
+      };
+      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes) * (kPair ? 2u : 1u);
       // weights are parameters: their first stages are requested before the dependency wait
       const int pre = a.epi.static_w ? min(a.stages, kb1 - kb0) : 0;
       for (int i = 0; i < pre; ++i) {
-        mbar_arrive_expect_tx(&full_bar[i], stage_bytes);
-        tma_load_2d(smem + i * stage_bytes, &tmap_w, &full_bar[i], (kb0 + i) * BK, n_blk * BW);
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[i], tx_bytes);
+        load(smem + i * stage_bytes, &tmap_w, i, (kb0 + i) * BK, n_blk * BW);
       }
       griddep_wait();
       int stage = 0;
@@ -100,43 +152,61 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       for (int kb = kb0; kb < kb1; ++kb) {
         uint8_t* st = smem + stage * stage_bytes;
         if (kb - kb0 >= pre) {
+          const long long c0 = dbg ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-          tma_load_2d(st, &tmap_w, &full_bar[stage], kb * BK, n_blk * BW);
+          if (dbg) w_empty += clock64() - c0;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          load(st, &tmap_w, stage, kb * BK, n_blk * BW);
         }
-        for (int r = 0; r < a.m_pad; r += 32)  // token tile as 32-row boxes (rows >= M are zero-filled)
-          tma_load_2d(st + BW * BK * 2 + r * 128, &tmap_x, &full_bar[stage], kb * BK, r);
+        uint8_t* xs = st + BW * BK * 2;
+        // one box per UMMA token chunk (rows >= M are zero-filled); a pair CTA stages its half
+        const int box = kPair ? a.chunk / 2 : a.chunk;
+        for (int n0 = 0, o = 0; n0 < a.m_pad; n0 += a.chunk, o += box)
+          load(xs + o * 128, &tmap_x, stage, kb * BK, n0 + static_cast<int>(rank) * box);
         if (++stage == a.stages) {
           stage = 0;
           phase ^= 1;
         }
       }
+      if (dbg) dbg[4] = w_empty;
     }
   } else if (warp == 1) {
-    if (lane == 0 && kb1 > kb0) {
+    if (lane == 0 && kb1 > kb0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_full = 0;
+      const long long m0 = dbg ? clock64() : 0;
       for (int kb = kb0; kb < kb1; ++kb) {
+        const long long c0 = dbg ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase);
+        if (dbg) w_full += clock64() - c0;
         tc_fence_after();
         const uint32_t wa = smem_u32(smem + stage * stage_bytes);
         const uint32_t xa = wa + BW * BK * 2;
-        for (int n0 = 0; n0 < a.m_pad; n0 += 256) {
-          const int nn = min(256, a.m_pad - n0);
-          const uint32_t idesc = make_idesc_bf16(BW, nn, 0, 0);
+        const uint32_t idesc = make_idesc_bf16(kPair ? 256 : 128, a.chunk, 0, 0);
+        for (int n0 = 0; n0 < a.m_pad; n0 += a.chunk) {
           const uint64_t ad = make_smem_desc(wa, 16, 1024, kLayoutSW128);
-          const uint64_t bd = make_smem_desc(xa + n0 * 128, 16, 1024, kLayoutSW128);
+          const uint64_t bd = make_smem_desc(xa + (kPair ? n0 / 2 : n0) * 128, 16, 1024, kLayoutSW128);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16(tmem_base + n0, ad + 2 * k, bd + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t acc = (kb != kb0 || k != 0) ? 1u : 0u;
+            if (kPair) umma_f16_pair(tmem_base + n0, ad + 2 * k, bd + 2 * k, idesc, acc);
+            else umma_f16(tmem_base + n0, ad + 2 * k, bd + 2 * k, idesc, acc);
+          }
         }
-        umma_commit(&empty_bar[stage]);
+        if (kPair) umma_commit_pair(&empty_bar[stage]);
+        else umma_commit(&empty_bar[stage]);
         if (++stage == a.stages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(acc_full);
+      if (kPair) umma_commit_pair(acc_full);
+      else umma_commit(acc_full);
+      if (dbg) {
+        dbg[2] = w_full;
+        dbg[3] = clock64() - m0;
+      }
     }
   } else {
     // ===================== epilogue =====================
@@ -145,16 +215,22 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     const int n_local = quad * 32 + lane;
     const int n = n_blk * BW + n_local;
     const bool n_ok = n < a.N;
+    const bool swiglu = a.epi.swiglu != 0;
+    const int act = a.epi.act;
     griddep_wait();
+    e0 = dbg ? clock64() : 0;
     if (kb1 > kb0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
     }
+    e1 = dbg ? clock64() : 0;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     bool finalize = true;
     const float* slots = nullptr;
     if (a.splits > 1) {
-      float* mine = a.ws + (static_cast<size_t>(unit) * a.m_pad) * BW + n_local;
+      const int my_unit = n_blk * a.splits + split;
+      float* mine = a.ws + (static_cast<size_t>(my_unit) * a.m_pad) * BW + n_local;
+#pragma unroll 1
       for (int c = 0; c < a.m_pad / 32; ++c) {
         uint32_t r[32];
         if (kb1 > kb0) {
@@ -182,11 +258,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     }
     if (finalize) {
       const float bias = (a.epi.bias != nullptr && n_ok) ? __bfloat162float(a.epi.bias[n]) : 0.f;
+      // output row geometry of this CTA: features [nc0, nc0 + row_elems)
+      const int row_elems = swiglu ? BW / 2 : BW;
+      const int nc0 = swiglu ? (n_blk * BW) >> 1 : n_blk * BW;
+      const int n_out = swiglu ? a.N >> 1 : a.N;
+      const int vpr = row_elems / 8;  // 16-byte vectors per token row
+#pragma unroll 1
       for (int c = 0; c < a.m_pad / 32; ++c) {
+        if (c * 32 >= a.M) break;
         float v[32];
         if (a.splits > 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll 1
           for (int s = 0; s < a.splits; ++s) {  // fixed order
             const float* sp = slots + (static_cast<size_t>(s) * a.m_pad + c * 32) * BW;
 #pragma unroll
@@ -199,93 +283,143 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         }
+        uint8_t* buf = stg + (c & 1) * (32 * kStgPitch);
+        if (swiglu) {
+          // lanes (2i, 2i+1) hold (gate_i, up_i) of the interleaved weight rows
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf) + (n_local >> 1);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int m = c * 32 + j;
-          float x = v[j] + bias;
-          if (a.epi.swiglu) {
-            // lanes (2i, 2i+1) hold (gate_i, up_i) of the interleaved weight rows
-            const float xb = bf16_round(x);
+          for (int j = 0; j < 32; ++j) {
+            const float xb = bf16_round(v[j] + bias);
             const float other = __shfl_xor_sync(0xffffffffu, xb, 1);
-            if (!(lane & 1) && n_ok && m < a.M)
-              a.C[static_cast<size_t>(m) * a.ldc + (n >> 1)] =
-                  __float2bfloat16(bf16_round(silu_f(xb)) * other);
-            continue;
+            if (!(lane & 1)) dst[j * (kStgPitch / 2)] = __float2bfloat16(bf16_round(silu_f(xb)) * other);
           }
-          if (a.epi.act != ACT_NONE) {
-            const float xb = bf16_round(x);
-            x = a.epi.act == ACT_GELU_TANH ? gelu_tanh_f(xb)
-                                           : (a.epi.act == ACT_GELU_ERF ? gelu_erf_f(xb) : silu_f(xb));
-          }
-          if (n_ok && m < a.M) {
-            if (a.epi.residual != nullptr) {
-              const int rr = a.epi.res_row_mod > 0 ? (m % a.epi.res_row_mod) : m;
-              x = bf16_round(x) + __bfloat162float(a.epi.residual[static_cast<size_t>(rr) * a.epi.ld_res + n]);
+        } else {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf) + n_local;
+          if (act == ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j * (kStgPitch / 2)] = __float2bfloat16(v[j] + bias);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float xb = bf16_round(v[j] + bias);
+              const float y = act == ACT_GELU_TANH ? gelu_tanh_f(xb)
+                                                   : (act == ACT_GELU_ERF ? gelu_erf_f(xb) : silu_f(xb));
+              dst[j * (kStgPitch / 2)] = __float2bfloat16(y);
             }
-            a.C[static_cast<size_t>(m) * a.ldc + n] = __float2bfloat16(x);
           }
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // transposed read-out: 16-byte vectors along the feature dimension
+        for (int q = epi_tid; q < 32 * vpr; q += 128) {
+          const int tok = q / vpr, seg = q - tok * vpr;
+          const int m = c * 32 + tok;
+          const int nn = nc0 + seg * 8;
+          if (m < a.M && nn < n_out) {
+            uint4 o = *reinterpret_cast<const uint4*>(buf + tok * kStgPitch + seg * 16);
+            if (a.epi.residual != nullptr) {
+              const int rr = a.epi.res_row_mod > 0 ? (m % a.epi.res_row_mod) : m;
+              const uint4 b = ldg_v4(a.epi.residual + static_cast<size_t>(rr) * a.epi.ld_res + nn);
+              o.x = pack_bf16(bf_lo(o.x) + bf_lo(b.x), bf_hi(o.x) + bf_hi(b.x));
+              o.y = pack_bf16(bf_lo(o.y) + bf_lo(b.y), bf_hi(o.y) + bf_hi(b.y));
+              o.z = pack_bf16(bf_lo(o.z) + bf_lo(b.z), bf_hi(o.z) + bf_hi(b.z));
+              o.w = pack_bf16(bf_lo(o.w) + bf_lo(b.w), bf_hi(o.w) + bf_hi(b.w));
+            }
+            stg_v4(a.C + static_cast<size_t>(m) * a.ldc + nn, o);
+          }
+        }
+        // (no second barrier: the next chunk writes the other staging buffer, and the barrier of
+        //  that iteration orders this read-out before the buffer is written again)
       }
     }
   }
 
+  if (dbg && threadIdx.x == 64) {
+    dbg[7] = e1 - e0;            // epilogue warps waiting for the accumulator
+    dbg[5] = clock64() - e1;     // epilogue proper
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();  // the leader's MMAs read the peer's shared memory until the end
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (kPair) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
+  if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
 }
 
-}  // namespace
-
-// returns -1 if the shape is not handled here
-int gemm_skinny_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
-                     int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
-  if (M > 512 || M < 1) return -1;
+template <bool kPair>
+int launch_skinny(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
+                  int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
   const int m_pad = (M + 31) / 32 * 32;
   const int sms = num_sms();
   const int n_blocks = (N + BW - 1) / BW;
+  const int nb_units = kPair ? (n_blocks + 1) / 2 : n_blocks;  // scheduling units along N
+  const int slots = kPair ? sms / 2 : sms;
   const int nkb = (K + BK - 1) / BK;
   int splits = 1;
-  if (n_blocks < sms) {
-    splits = (sms + n_blocks / 2) / n_blocks;
+  if (nb_units < slots) {
+    splits = (slots + nb_units / 2) / nb_units;
     if (splits > 8) splits = 8;
     while (splits > 1 && nkb / splits < 4) --splits;
   }
-  const int kb_per_split = (nkb + splits - 1) / splits;
+  int kb_per_split = (nkb + splits - 1) / splits;
   splits = (nkb + kb_per_split - 1) / kb_per_split;  // no empty splits
   void* ws_ptr = nullptr;
   size_t ws_bytes = 0;
   get_workspace(&ws_ptr, &ws_bytes);
-  const size_t need = kCounterBytes + static_cast<size_t>(n_blocks) * splits * m_pad * BW * 4;
-  if (splits > 1 && (ws_ptr == nullptr || ws_bytes < need || n_blocks > 16384)) {
+  const int n_blocks_alloc = kPair ? nb_units * 2 : n_blocks;
+  const size_t need = kCounterBytes + static_cast<size_t>(n_blocks_alloc) * splits * m_pad * BW * 4;
+  if (splits > 1 && (ws_ptr == nullptr || ws_bytes < need || n_blocks_alloc > 16384)) {
     splits = 1;
+    kb_per_split = nkb;
   }
   SkinnyArgs a;
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
   a.m_pad = m_pad;
+  a.chunk = m_pad > 256 ? m_pad / 2 : m_pad;  // multiple of 16; pair halves are multiples of 8 rows
   a.splits = splits;
-  a.kb_per_split = splits > 1 ? kb_per_split : nkb;
+  a.kb_per_split = kb_per_split;
   a.counters = static_cast<int*>(ws_ptr);
   a.ws = ws_ptr ? reinterpret_cast<float*>(static_cast<char*>(ws_ptr) + kCounterBytes) : nullptr;
   a.epi = epi;
-  const int stage_bytes = BW * BK * 2 + m_pad * BK * 2;
-  int stages = (216 * 1024) / stage_bytes;
+  a.dbg = nullptr;
+  if (const char* e = getenv("VILA_B200_GEMM_DEBUG")) {  // profiling aid: hex device pointer
+    unsigned long long ptr = 0;
+    if (sscanf(e, "%llx", &ptr) == 1) a.dbg = reinterpret_cast<long long*>(ptr);
+  }
+  const int x_rows = kPair ? m_pad / 2 : m_pad;
+  const int stage_bytes = BW * BK * 2 + x_rows * BK * 2;
+  const int budget = 227 * 1024 - 1024 - kStgBytes - 256;
+  int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return -1;
   a.stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 8 * 8 * 2 + 64 + 1024;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + kStgBytes + 256 + 1024;
   CUtensorMap tw, tx;
   if (make_tmap_2d_bf16(&tw, W, N, K, ldw, BW, BK, 128)) return 1;
-  if (make_tmap_2d_bf16(&tx, A, M, K, lda, 32, BK, 128)) return 1;
+  if (make_tmap_2d_bf16(&tx, A, M, K, lda, kPair ? a.chunk / 2 : a.chunk, BK, 128)) return 1;
+  auto kern = gemm_skinny_kernel<kPair>;
   static bool attr = false;
   if (!attr) {
-    VB_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  VB_CUDA(launch_pdl(gemm_skinny_kernel, dim3(n_blocks * splits), dim3(kThreads), smem, stream, tw, tx, a));
+  const int grid = nb_units * splits * (kPair ? 2 : 1);
+  VB_CUDA(launch_pdl_cluster(kern, dim3(grid), dim3(kThreads), smem, stream, dim3(kPair ? 2 : 1, 1, 1),
+                             tw, tx, a));
   return 0;
+}
+
+}  // namespace
+
+// returns -1 if the shape is not handled here.  pair: 0 = one CTA per 128 weight rows,
+// 1 = CTA pairs (tcgen05 cta_group::2) per 256 weight rows
+int gemm_skinny_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
+                     int ldc, int M, int N, int K, const GemmEpilogue& epi, int pair, cudaStream_t stream) {
+  if (M > 512 || M < 1) return -1;
+  return pair ? launch_skinny<true>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream)
+              : launch_skinny<false>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
 }
 
 }  // namespace vb

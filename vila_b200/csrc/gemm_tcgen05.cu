@@ -30,10 +30,15 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one 128B-swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..5: epilogue
 
-template <int BLOCK_N, int kStages>
+// kPair: a 2-CTA cluster computes one (2*BLOCK_M) x BLOCK_N tile with tcgen05.mma.cta_group::2 —
+// each CTA stages its own 128 rows of A and HALF of the W tile (BLOCK_N/2 rows); the tensor cores of
+// both SMs read both halves, so the bytes each SM pulls through its L2 port per MAC drop by 1/3
+// (128x256 tile: 48 KB -> 32 KB per k-block), which is what bounds the single-CTA kernel.
+template <int BLOCK_N, int kStages, bool kPair = false>
 struct GemmSmem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kBRows = kPair ? BLOCK_N / 2 : BLOCK_N;  // W rows staged by one CTA
+  static constexpr int kBBytes = kBRows * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + align slack
@@ -67,15 +72,20 @@ struct Sched {
   int stream_k;
   long it, it_end;  // stream-K
   int tile;         // data-parallel
-  __device__ __forceinline__ Sched(int M, int N, int K, int block_n, int stream_k_) {
+  int stride;  // data-parallel: tiles between two visits of this CTA (or CTA pair)
+  // tile_m: rows of one scheduling tile (128, or 256 for a CTA pair); worker/n_workers: index and
+  // number of the units that walk the tile list (CTAs, or CTA pairs)
+  __device__ __forceinline__ Sched(int M, int N, int K, int block_n, int stream_k_, int tile_m = BLOCK_M,
+                                   int worker = blockIdx.x, int n_workers = gridDim.x) {
     nkb = (K + BLOCK_K - 1) / BLOCK_K;
-    num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+    num_m_blocks = (M + tile_m - 1) / tile_m;
     num_tiles = num_m_blocks * ((N + block_n - 1) / block_n);
     stream_k = stream_k_;
     const long total = static_cast<long>(num_tiles) * nkb;
-    it = total * blockIdx.x / gridDim.x;
-    it_end = total * (blockIdx.x + 1) / gridDim.x;
-    tile = blockIdx.x;
+    it = total * worker / n_workers;
+    it_end = total * (worker + 1) / n_workers;
+    tile = worker;
+    stride = n_workers;
   }
   // returns false when done; otherwise the next segment
   __device__ __forceinline__ bool next(int& t, int& kb0, int& kb1) {
@@ -92,17 +102,18 @@ struct Sched {
     t = tile;
     kb0 = 0;
     kb1 = nkb;
-    tile += gridDim.x;
+    tile += stride;
     return true;
   }
 };
 
-template <int BLOCK_N, int kStages>
+template <int BLOCK_N, int kStages, bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_w, __nv_bfloat16* __restrict__ C,
                          int ldc, int M, int N, int K, GemmEpilogue epi) {
-  using S = GemmSmem<BLOCK_N, kStages>;
+  using S = GemmSmem<BLOCK_N, kStages, kPair>;
+  constexpr int TILE_M = kPair ? 2 * BLOCK_M : BLOCK_M;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -117,8 +128,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
-  const int stream_k = epi.split_k > 1 ? 1 : 0;
+  const int num_m_blocks = (M + TILE_M - 1) / TILE_M;
+  const int stream_k = (!kPair && epi.split_k > 1) ? 1 : 0;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -130,15 +144,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 128);
-    mbar_init(&tmem_empty[1], 128);
+    // pair: one arrival per epilogue warp of BOTH CTAs, on the leader's barrier
+    mbar_init(&tmem_empty[0], kPair ? 8 : 128);
+    mbar_init(&tmem_empty[1], kPair ? 8 : 128);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc<2 * BLOCK_N>(tmem_ptr);
+    if (kPair) tmem_alloc_pair<2 * BLOCK_N>(tmem_ptr);
+    else tmem_alloc<2 * BLOCK_N>(tmem_ptr);
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();  // the peer's barriers exist before any remote signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   griddep_launch_dependents();
@@ -146,7 +163,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      Sched sch(M, N, K, BLOCK_N, stream_k);
+      Sched sch(M, N, K, BLOCK_N, stream_k, TILE_M, worker, n_workers);
+      // every load of a pair reports to the LEADER's full barrier, which expects both CTAs' bytes
+      auto load = [&](void* dst, const CUtensorMap* tm, int i, int c0, int c1) {
+        if (kPair) tma_load_2d_pair(dst, tm, mapa_u32(smem_u32(&full_bar[i]), 0), c0, c1);
+        else tma_load_2d(dst, tm, &full_bar[i], c0, c1);
+      };
+      constexpr uint32_t kTxBytes = S::kStageBytes * (kPair ? 2 : 1);
+      const int a_row_off = static_cast<int>(rank) * BLOCK_M;
+      const int w_row_off = static_cast<int>(rank) * S::kBRows;
       int stage = 0;
       uint32_t phase = 0;
       int t, kb0, kb1;
@@ -160,9 +185,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         pre = min(kStages, pkb1 - pkb0);
         const int n_blk = pt / num_m_blocks;
         for (int i = 0; i < pre; ++i) {
-          mbar_arrive_expect_tx(&full_bar[i], S::kStageBytes);
-          tma_load_2d(smem_b + i * S::kBBytes, &tmap_w, &full_bar[i], (pkb0 + i) * BLOCK_K,
-                      n_blk * BLOCK_N);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[i], kTxBytes);
+          load(smem_b + i * S::kBBytes, &tmap_w, i, (pkb0 + i) * BLOCK_K, n_blk * BLOCK_N + w_row_off);
         }
       }
       griddep_wait();
@@ -175,15 +199,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = kb0; kb < kb1; ++kb) {
           if (first && (kb - kb0) < pre) {
             // W already in flight for this stage: only A is missing
-            tma_load_2d(smem_a + stage * S::kABytes, &tmap_a, &full_bar[stage], kb * BLOCK_K,
-                        m_blk * BLOCK_M);
+            load(smem_a + stage * S::kABytes, &tmap_a, stage, kb * BLOCK_K, m_blk * TILE_M + a_row_off);
           } else {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-            tma_load_2d(smem_a + stage * S::kABytes, &tmap_a, &full_bar[stage], kb * BLOCK_K,
-                        m_blk * BLOCK_M);
-            tma_load_2d(smem_b + stage * S::kBBytes, &tmap_w, &full_bar[stage], kb * BLOCK_K,
-                        n_blk * BLOCK_N);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], kTxBytes);
+            load(smem_a + stage * S::kABytes, &tmap_a, stage, kb * BLOCK_K, m_blk * TILE_M + a_row_off);
+            load(smem_b + stage * S::kBBytes, &tmap_w, stage, kb * BLOCK_K, n_blk * BLOCK_N + w_row_off);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -195,9 +216,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
-      Sched sch(M, N, K, BLOCK_N, stream_k);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
+      Sched sch(M, N, K, BLOCK_N, stream_k, TILE_M, worker, n_workers);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -217,16 +238,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) along K inside the 128B swizzle atom: +2 in addr>>4 units
-            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                     (kb != kb0 || k != 0) ? 1u : 0u);
+            const uint32_t acc = (kb != kb0 || k != 0) ? 1u : 0u;
+            if (kPair) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+            else umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          // frees this smem stage (in both CTAs of a pair) when the MMAs retire
+          if (kPair) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        if (kPair) umma_commit_pair(&tmem_full[as]);  // accumulator complete -> epilogue(s)
+        else umma_commit(&tmem_full[as]);
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -237,7 +262,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ===================== epilogue warps (TMEM -> regs -> global) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int epi_tid = threadIdx.x - 64;
-    Sched sch(M, N, K, BLOCK_N, stream_k);
+    Sched sch(M, N, K, BLOCK_N, stream_k, TILE_M, worker, n_workers);
     int as = 0;
     uint32_t aphase = 0;
     int t, kb0, kb1;
@@ -247,7 +272,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_blk = t / num_m_blocks;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      const int row = m_blk * TILE_M + static_cast<int>(rank) * BLOCK_M + quad * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N;
       const bool partial = (kb0 != 0) || (kb1 != sch.nkb);
@@ -406,7 +431,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       if (!partial) {
         tc_fence_before();
-        mbar_arrive(&tmem_empty[as]);
+        if (kPair) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
+        } else {
+          mbar_arrive(&tmem_empty[as]);
+        }
       }
       if (++as == 2) {
         as = 0;
@@ -416,10 +446,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();  // the leader's MMAs read the peer's shared memory until the end
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * BLOCK_N>(tmem_base);
+    if (kPair) tmem_dealloc_pair<2 * BLOCK_N>(tmem_base);
+    else tmem_dealloc<2 * BLOCK_N>(tmem_base);
   }
 }
 
@@ -431,22 +463,31 @@ struct Workspace {
 Workspace g_ws;
 constexpr size_t kCounterBytes = 64 * 1024;  // 16384 tile counters
 
-template <int BLOCK_N, int kStages>
+template <int BLOCK_N, int kStages, bool kPair = false>
 int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
                 int ldc, int M, int N, int K, GemmEpilogue epi, int force_stream_k,
                 cudaStream_t stream) {
-  using S = GemmSmem<BLOCK_N, kStages>;
+  using S = GemmSmem<BLOCK_N, kStages, kPair>;
+  constexpr int TILE_M = kPair ? 2 * BLOCK_M : BLOCK_M;
   CUtensorMap ta, tw;
   if (make_tmap_2d_bf16(&ta, A, M, K, lda, BLOCK_M, BLOCK_K, 128)) return 1;
-  if (make_tmap_2d_bf16(&tw, W, N, K, ldw, BLOCK_N, BLOCK_K, 128)) return 1;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, kStages>;
+  if (make_tmap_2d_bf16(&tw, W, N, K, ldw, S::kBRows, BLOCK_K, 128)) return 1;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, kStages, kPair>;
   static bool attr_set = false;
   if (!attr_set) {
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
   const int sms = num_sms();
-  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int tiles = ((M + TILE_M - 1) / TILE_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  if (kPair) {
+    // data-parallel over 256 x BLOCK_N tiles, one tile at a time per CTA pair
+    const int pairs = tiles < sms / 2 ? tiles : sms / 2;
+    epi.split_k = 1;
+    VB_CUDA(launch_pdl_cluster(kern, dim3(2 * pairs), dim3(kNumThreads), S::kTotal, stream,
+                               dim3(2, 1, 1), ta, tw, C, ldc, M, N, K, epi));
+    return 0;
+  }
   const int nkb = (K + BLOCK_K - 1) / BLOCK_K;
   // stream-K when whole tiles would leave SMs idle or produce a ragged last wave
   bool sk = false;
@@ -526,13 +567,16 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
   return launch_gemm<128, 6>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
 }
 
-// test hook: force a tile configuration (block_n in {64,128,256}; +1000 forces stream-K, +2000 off)
+// test hook: force a tile configuration (block_n in {64,128,256}; +1000 forces stream-K, +2000 off;
+// 3000 / 3001: swap-AB skinny kernel, single CTA / CTA pair; 4128 / 4256: CTA-pair 256 x BLOCK_N tiles)
 int gemm_bf16_cfg(int block_n, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw,
                   __nv_bfloat16* C, int ldc, int M, int N, int K, const GemmEpilogue& epi,
                   cudaStream_t stream) {
   if (check_args(A, lda, W, ldw, C, ldc, M, N, K, epi)) return 1;
-  if (block_n == 3000) {
-    const int rc = gemm_skinny_bf16(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
+  if (block_n == 4256) return launch_gemm<256, 6, true>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
+  if (block_n == 4128) return launch_gemm<128, 8, true>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
+  if (block_n == 3000 || block_n == 3001) {
+    const int rc = gemm_skinny_bf16(A, lda, W, ldw, C, ldc, M, N, K, epi, block_n - 3000, stream);
     if (rc < 0) set_last_error("gemm_bf16_cfg: skinny kernel does not handle M=%d", M);
     return rc < 0 ? 1 : rc;
   }

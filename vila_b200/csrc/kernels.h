@@ -27,7 +27,7 @@ struct GemmEpilogue {
 int set_workspace(void* ptr, size_t bytes);
 void get_workspace(void** ptr, size_t* bytes);
 int gemm_skinny_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
-                     int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream);  // -1: not handled
+                     int ldc, int M, int N, int K, const GemmEpilogue& epi, int pair, cudaStream_t stream);  // -1: not handled
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
               int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream);
 int gemm_bf16_cfg(int block_n, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw,
