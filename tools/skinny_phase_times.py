@@ -11,6 +11,8 @@ dbg = torch.zeros(8 * 4096, dtype=torch.int64, device="cuda")
 os.environ["VILA_B200_GEMM_DEBUG"] = "%x" % dbg.data_ptr()
 out = {}
 shapes = {"llm_gu": (279, 37888, 3584), "llm_down": (279, 3584, 18944), "llm_qkv": (279, 4608, 3584)}
+if "--sweep" in sys.argv:  # tensor-pipe time per k-block as a function of the token count (UMMA N)
+    shapes = {f"m{m}": (m, 18944, 3584) for m in (64, 128, 144, 192, 256, 288, 320, 384, 512)}
 for name, (M, N, K) in shapes.items():
     x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
     ws = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) / math.sqrt(K) for _ in range(3)]
@@ -34,6 +36,8 @@ for name, (M, N, K) in shapes.items():
             "epilogue_kcyc_mean": round(float(d[:, 5].float().mean()) / 1e3, 1),
             "sms_used": int(d[:, 6].unique().numel()),
         }
+        nkb_cta = (K + 63) // 64 / max(1, row["ctas"] // ((N + 127) // 128))
+        row["mma_busy_cyc_per_kblock"] = round((row["mma_loop_kcyc_mean"] - row["mma_wait_full_kcyc_mean"]) * 1e3 / nkb_cta)
         out[f"{name}/{cfg}"] = row
         print(name, cfg, row, flush=True)
 Path("gpurun_out").mkdir(exist_ok=True)

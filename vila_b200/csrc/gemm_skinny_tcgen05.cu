@@ -60,6 +60,7 @@ struct SkinnyArgs {
   int stages;
   int splits;       // k-splits per weight block (pair mode: per pair of weight blocks)
   int kb_per_split;
+  int cluster_k;    // 1: the splits of a weight block form a cluster and reduce through DSMEM
   float* ws;        // [n_blk][split][m_pad][128] fp32 partials
   int* counters;    // [n_blocks]
   GemmEpilogue epi;
@@ -208,15 +209,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         dbg[3] = clock64() - m0;
       }
     }
-  } else {
-    // ===================== epilogue =====================
-    const int quad = warp & 3;
-    const int epi_tid = threadIdx.x - 64;
-    const int n_local = quad * 32 + lane;
-    const int n = n_blk * BW + n_local;
-    const bool n_ok = n < a.N;
-    const bool swiglu = a.epi.swiglu != 0;
-    const int act = a.epi.act;
+  }
+  // ===================== epilogue warps (2..5) =====================
+  const int quad = warp & 3;
+  const int epi_tid = threadIdx.x - 64;
+  const int n_local = quad * 32 + lane;
+  const int n = n_blk * BW + n_local;
+  const bool n_ok = n < a.N;
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+  bool finalize = true;
+  const float* slots = nullptr;
+  float* dump = reinterpret_cast<float*>(smem);  // cluster split-K: [token][128] fp32 partial
+  if (warp >= 2) {
+    // ---- phase 1: wait for the accumulator; split-K partials leave TMEM ----
     griddep_wait();
     e0 = dbg ? clock64() : 0;
     if (kb1 > kb0) {
@@ -224,10 +229,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       tc_fence_after();
     }
     e1 = dbg ? clock64() : 0;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    bool finalize = true;
-    const float* slots = nullptr;
-    if (a.splits > 1) {
+    if (a.splits > 1 && a.cluster_k) {
+      // All of THIS CTA's MMAs have retired -> its pipeline stages are dead; park the partial there.
+      // (Peers PULL it after the cluster barrier: pushing into a peer would race with the peer's
+      //  still-running main loop.)
+#pragma unroll 1
+      for (int c = 0; c < a.m_pad / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dump[(c * 32 + j) * BW + n_local] = __uint_as_float(r[j]);
+      }
+    } else if (a.splits > 1) {
       const int my_unit = n_blk * a.splits + split;
       float* mine = a.ws + (static_cast<size_t>(my_unit) * a.m_pad) * BW + n_local;
 #pragma unroll 1
@@ -256,18 +270,40 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       if (finalize) __threadfence();
       slots = a.ws + (static_cast<size_t>(n_blk) * a.splits * a.m_pad) * BW + n_local;
     }
-    if (finalize) {
+  }
+  // cluster split-K: the `splits` CTAs of one weight block form a cluster; once every partial is
+  // parked, CTA r reduces the 32-token chunks c with c % splits == r straight out of its peers'
+  // shared memory (DSMEM loads) in a fixed order — no workspace round trip, no counters, deterministic
+  if (a.cluster_k) cluster_sync_all();
+  if (warp >= 2 && finalize) {
+    // ---- phase 2: bias / activation / transposition / store ----
+    const bool swiglu = a.epi.swiglu != 0;
+    const int act = a.epi.act;
+    const bool dsmem = a.cluster_k && a.splits > 1;
+    {
       const float bias = (a.epi.bias != nullptr && n_ok) ? __bfloat162float(a.epi.bias[n]) : 0.f;
       // output row geometry of this CTA: features [nc0, nc0 + row_elems)
       const int row_elems = swiglu ? BW / 2 : BW;
       const int nc0 = swiglu ? (n_blk * BW) >> 1 : n_blk * BW;
       const int n_out = swiglu ? a.N >> 1 : a.N;
       const int vpr = row_elems / 8;  // 16-byte vectors per token row
+      const int c_first = dsmem ? split : 0, c_step = dsmem ? a.splits : 1;
+      int it = 0;
 #pragma unroll 1
-      for (int c = 0; c < a.m_pad / 32; ++c) {
+      for (int c = c_first; c < a.m_pad / 32; c += c_step, ++it) {
         if (c * 32 >= a.M) break;
         float v[32];
-        if (a.splits > 1) {
+        if (dsmem) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          const uint32_t off = smem_u32(dump) + static_cast<uint32_t>((c * 32) * BW + n_local) * 4u;
+#pragma unroll 1
+          for (int s = 0; s < a.splits; ++s) {  // fixed order: rank 0 (lowest k) first
+            const uint32_t base = mapa_u32(off, static_cast<uint32_t>(s));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += ld_dsmem_f32(base + j * (BW * 4));
+          }
+        } else if (a.splits > 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
 #pragma unroll 1
@@ -283,15 +319,22 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         }
-        uint8_t* buf = stg + (c & 1) * (32 * kStgPitch);
+        uint8_t* buf = stg + (it & 1) * (32 * kStgPitch);
         if (swiglu) {
           // lanes (2i, 2i+1) hold (gate_i, up_i) of the interleaved weight rows
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf) + (n_local >> 1);
+          // The pair splits the 32 tokens: the even (gate) lane finishes tokens 0..15, the odd (up)
+          // lane tokens 16..31, so every lane does useful SiLU work and one shuffle serves two tokens.
+          const bool odd = (lane & 1) != 0;
+          __nv_bfloat16* dst =
+              reinterpret_cast<__nv_bfloat16*>(buf) + (n_local >> 1) + (odd ? 16 * (kStgPitch / 2) : 0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float xb = bf16_round(v[j] + bias);
-            const float other = __shfl_xor_sync(0xffffffffu, xb, 1);
-            if (!(lane & 1)) dst[j * (kStgPitch / 2)] = __float2bfloat16(bf16_round(silu_f(xb)) * other);
+          for (int j = 0; j < 16; ++j) {
+            const float a0 = bf16_round(v[j] + bias);       // this lane's row, token j
+            const float a1 = bf16_round(v[16 + j] + bias);  // this lane's row, token 16 + j
+            const float recv = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
+            const float gate = odd ? recv : a0;
+            const float up = odd ? a1 : recv;
+            dst[j * (kStgPitch / 2)] = __float2bfloat16(bf16_round(silu_f(gate)) * up);
           }
         } else {
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf) + n_local;
@@ -338,7 +381,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     dbg[5] = clock64() - e1;     // epilogue proper
   }
   tc_fence_before();
-  if (kPair) cluster_sync_all();  // the leader's MMAs read the peer's shared memory until the end
+  // pair: the leader's MMAs read the peer's shared memory until the end; cluster split-K: peers read
+  // this CTA's parked partial until they are done
+  if (kPair || a.cluster_k) cluster_sync_all();
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -365,6 +410,7 @@ int launch_skinny(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int l
   }
   int kb_per_split = (nkb + splits - 1) / splits;
   splits = (nkb + kb_per_split - 1) / kb_per_split;  // no empty splits
+  const int want_splits = splits;
   void* ws_ptr = nullptr;
   size_t ws_bytes = 0;
   get_workspace(&ws_ptr, &ws_bytes);
@@ -374,8 +420,58 @@ int launch_skinny(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int l
     splits = 1;
     kb_per_split = nkb;
   }
+  const int x_rows = kPair ? m_pad / 2 : m_pad;
+  const int stage_bytes = BW * BK * 2 + x_rows * BK * 2;
+  const int budget = 227 * 1024 - 1024 - kStgBytes - 256;
+  int stages = budget / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return -1;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + kStgBytes + 256 + 1024;
+  auto kern = gemm_skinny_kernel<kPair>;
+  static bool attr = false;
+  if (!attr) {
+    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  // cluster split-K (single-CTA flavour): largest split count whose clusters are all co-resident
+  int cluster_k = 0;
+  if (!kPair && want_splits > 1) {
+    static int active[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+    for (int sp = want_splits; sp >= 2; --sp) {
+      const int kbps = (nkb + sp - 1) / sp;
+      if ((nkb + kbps - 1) / kbps != sp) continue;
+      // the fp32 partial (m_pad x 128) is parked in the dead pipeline stages
+      if (static_cast<size_t>(m_pad) * BW * 4 > static_cast<size_t>(stages) * stage_bytes) continue;
+      if (active[sp] < 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(sp * 64);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = sp;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n_act = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_act, kern, &cfg) != cudaSuccess) {
+          (void)cudaGetLastError();
+          n_act = 0;
+        }
+        active[sp] = n_act;
+      }
+      if (active[sp] >= n_blocks) {
+        splits = sp;
+        kb_per_split = kbps;
+        cluster_k = 1;
+        break;
+      }
+    }
+  }
   SkinnyArgs a;
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
+  a.cluster_k = cluster_k;
   a.m_pad = m_pad;
   a.chunk = m_pad > 256 ? m_pad / 2 : m_pad;  // multiple of 16; pair halves are multiples of 8 rows
   a.splits = splits;
@@ -388,26 +484,13 @@ int launch_skinny(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int l
     unsigned long long ptr = 0;
     if (sscanf(e, "%llx", &ptr) == 1) a.dbg = reinterpret_cast<long long*>(ptr);
   }
-  const int x_rows = kPair ? m_pad / 2 : m_pad;
-  const int stage_bytes = BW * BK * 2 + x_rows * BK * 2;
-  const int budget = 227 * 1024 - 1024 - kStgBytes - 256;
-  int stages = budget / stage_bytes;
-  if (stages > 8) stages = 8;
-  if (stages < 2) return -1;
   a.stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + kStgBytes + 256 + 1024;
   CUtensorMap tw, tx;
   if (make_tmap_2d_bf16(&tw, W, N, K, ldw, BW, BK, 128)) return 1;
   if (make_tmap_2d_bf16(&tx, A, M, K, lda, kPair ? a.chunk / 2 : a.chunk, BK, 128)) return 1;
-  auto kern = gemm_skinny_kernel<kPair>;
-  static bool attr = false;
-  if (!attr) {
-    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
   const int grid = nb_units * splits * (kPair ? 2 : 1);
-  VB_CUDA(launch_pdl_cluster(kern, dim3(grid), dim3(kThreads), smem, stream, dim3(kPair ? 2 : 1, 1, 1),
-                             tw, tx, a));
+  VB_CUDA(launch_pdl_cluster(kern, dim3(grid), dim3(kThreads), smem, stream,
+                             dim3(kPair ? 2 : (cluster_k ? splits : 1), 1, 1), tw, tx, a));
   return 0;
 }
 

@@ -558,8 +558,21 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
   // Measured on B200 (tools/bench_gemm.py): 128x256 tiles win as soon as they fill ~70 % of the
   // SMs (the 256-wide tile keeps the MMA, not shared-memory bandwidth, the limiter); otherwise
   // 128x128; 64-wide tiles only for narrow outputs.
+  // Few tokens (short-prompt prefill, projector): the weights dominate the traffic -> swap-AB kernel
+  // (every weight byte enters an SM once; cluster split-K fills the machine).  B200, M = 279:
+  // down-proj 52 vs 90 us, gate/up 83 vs 86, qkv/o 21-23 vs 22 (profiles/r01_gemm_configs.md)
+  if (M <= 384) {
+    const int rc = gemm_skinny_bf16(A, lda, W, ldw, C, ldc, M, N, K, epi, 0, stream);
+    if (rc >= 0) return rc;
+  }
   const int sms = num_sms();
   const int mb = (M + BLOCK_M - 1) / BLOCK_M;
+  // CTA pairs (256 x 256 tiles, cta_group::2) once they fill ~85 % of the SM pairs: fewer bytes per
+  // MAC through each SM's L2 port and shared memory (8192^3: 752 vs 859 us; 2048x37888x3584: 355 vs 396)
+  const long pair_tiles = static_cast<long>((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + 255) / 256);
+  const long m_pad_pair = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (2L * BLOCK_M), m_pad_single = static_cast<long>(mb) * BLOCK_M;
+  if (pair_tiles * 20 >= 17L * (sms / 2) && m_pad_pair * 8 <= m_pad_single * 9)  // no extra row padding
+    return launch_gemm<256, 6, true>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
   const long tiles256 = static_cast<long>(mb) * ((N + 255) / 256);
   if (tiles256 * 10 >= 7L * sms)
     return launch_gemm<256, 4>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
