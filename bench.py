@@ -264,7 +264,7 @@ def run_ours(args):
                              "per decoded token" % (_lib.LAUNCHES - launches0,
                                                     llm.decoder(NEW_TOKENS).launches_per_step),
         "clocks": clock_summary,
-        "roofline": {"kernel": "gemv_kernel<8> (gate/up SwiGLU GEMV, N=%d K=%d, fused RMSNorm prologue)"
+        "roofline": {"kernel": "gemv_tma_kernel (gate/up SwiGLU GEMV, N=%d K=%d, fused RMSNorm prologue)"
                                % (2 * lc.intermediate_size, lc.hidden_size),
                      "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic,

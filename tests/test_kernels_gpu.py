@@ -36,6 +36,10 @@ def rb(x):  # round-trip through bf16 (emulate the reference's bf16 tensor betwe
 # ------------------------------------------------------------------------------------------------
 # GEMM
 # ------------------------------------------------------------------------------------------------
+def _tiles128(M, N):
+    return ((M + 127) // 128) * ((N + 127) // 128)
+
+
 GEMM_SHAPES = [
     (128, 128, 64), (256, 256, 128), (1024, 1152, 1152), (280, 3584, 3584), (1000, 4304, 1152),
     (1024, 1152, 4304), (2048, 1152, 592), (24, 512, 1536), (257, 3584, 4608), (130, 136, 72),
@@ -43,10 +47,12 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("block_n", [None, 64, 128, 256, 1064, 1128, 1256, 3000, 3001, 4128, 4256])  # 1000+: stream-K, 3000/3001: skinny single / CTA pair, 4xxx: CTA-pair tiles
+@pytest.mark.parametrize("block_n", [None, 64, 128, 256, 1064, 1128, 1256, 3000, 3001, 4128, 4256, 5128])  # 1000+: stream-K, 3000/3001: skinny single / CTA pair, 4xxx: CTA-pair tiles, 5128: split-K pairs
 def test_linear_plain(cuda, M, N, K, block_n):
     if block_n in (3000, 3001) and M > 512:
         pytest.skip("skinny kernel handles M <= 512")
+    if block_n == 5128 and (_tiles128(M, N) > 74 or K <= 64):
+        pytest.skip("split-K pairs: one tile per SM pair, >= 2 k-blocks")
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     x = bf(torch.randn(M, K, device=cuda, generator=g))
@@ -89,7 +95,7 @@ def test_linear_streamk_epilogues_and_workspace_is_clean(cuda):
         w = bf(torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K))
         b = bf(torch.randn(N, device=cuda, generator=g))
         res = bf(torch.randn(M, N, device=cuda, generator=g))
-        for bn in (1064, 1128, 1256, 4128, 4256) + ((3000, 3001) if M <= 512 else ()):
+        for bn in (1064, 1128, 1256, 4128, 4256) + ((3000, 3001) if M <= 512 else ()) + ((5128,) if _tiles128(M, N) <= 74 else ()):
             out = ops.linear(x, w, b, act=1, residual=res, block_n=bn, static_w=True)
             assert torch.equal(out, ops.linear(x, w, b, act=1, residual=res, block_n=bn, static_w=True))
             ref = rb(rb(O.gelu_tanh(rb(x.float() @ w.float().t() + b.float()))) + res.float())

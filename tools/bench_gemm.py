@@ -40,7 +40,7 @@ for name, (M, N, K) in shapes.items():
         return ws[idx[0]]
     us = timeit(lambda: torch.matmul(x, nxt().t(), out=out), reps=5 if name == "big" else 20)
     row = {"cublas_us": round(us, 2), "cublas_tflops": round(2 * M * N * K / us / 1e6, 1)}
-    for cfg in (None, 2128, 2256, 4128, 4256) + ((3000, 3001) if M <= 512 else ()):
+    for cfg in (None, 2128, 2256, 4128, 4256) + ((3000, 3001) if M <= 512 else ()) + ((5128,) if ((M + 127) // 128) * ((N + 127) // 128) <= 74 else ()):
         try:
             us = timeit(lambda: ops.linear(x, nxt(), out=out, block_n=cfg, static_w=True), reps=5 if name == "big" else 20)
             row[str(cfg)] = round(us, 2)

@@ -66,6 +66,21 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- activations (shared by the GEMM / GEMV epilogues).  The division is the fast one
+// (MUFU.RCP + FMUL, ~1 ulp): the IEEE fp32 division's slow path cost ~20 instructions per element
+// in the epilogues, and every result is rounded to bf16 right after.
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // gelu_pytorch_tanh: 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (x + k1 * x * x * x);
+  const float t = 1.0f - __fdividef(2.0f, __expf(2.0f * u) + 1.0f);
+  return 0.5f * x * (1.0f + t);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
+}
+
 // ---- programmatic dependent launch (PDL) device side ----
 // wait: all prerequisite grids have completed and their memory is visible (no-op without PDL)
 __device__ __forceinline__ void griddep_wait() {
@@ -241,6 +256,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
   float v;
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr));
+  return v;
+}
+__device__ __forceinline__ float4 ld_dsmem_v4f(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(cluster_addr));
   return v;
 }
 __device__ __forceinline__ void st_dsmem_u32(uint32_t cluster_addr, uint32_t v) {

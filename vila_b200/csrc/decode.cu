@@ -21,7 +21,6 @@ constexpr int kGemvThreads = 512;
 constexpr int kGemvWarps = kGemvThreads / 32;
 constexpr size_t kGemvPrefetchBytes = 256 * 1024;  // per-CTA L2 prefetch before the PDL wait
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc) {
   acc = fmaf(bf_lo(w.x), bf_lo(x.x), acc);

@@ -30,7 +30,6 @@ constexpr int SLOT = 7168;       // bytes per slot (one 3584-element bf16 row)
 constexpr int MD = 128;          // head dim
 constexpr int ACC_FLOATS = 2304;
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc) {
   acc = fmaf(bf_lo(w.x), bf_lo(x.x), acc);
   acc = fmaf(bf_hi(w.x), bf_hi(x.x), acc);

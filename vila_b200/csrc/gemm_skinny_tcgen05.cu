@@ -21,10 +21,10 @@
 //   warp 0: TMA producer (W tile 128x64 + token rows x 64 per k-block, 128B swizzle)
 //   warp 1: tcgen05.mma issuer (leader CTA only in pair mode) + TMEM allocator
 //           (accumulator: 128 lanes x M_pad fp32 columns per CTA)
-//   warps 2-5: epilogue — TMEM lane == output feature n, column == token m.  32-token chunks are
-//              transposed through a double-buffered shared-memory staging tile so that C[m, n0..]
-//              leaves the SM as 16-byte vectors in 256-byte rows; bias / GELU / residual / SwiGLU
-//              with the rounding points of gemm_tcgen05.cu.
+//   warps 2-9: epilogue, two warpgroups taking alternate 32-token chunks — TMEM lane == output
+//              feature n, column == token m.  Each chunk is transposed through a shared-memory
+//              staging tile so that C[m, n0..] leaves the SM as 16-byte vectors in 256-byte rows;
+//              bias / GELU / residual / SwiGLU with the rounding points of gemm_tcgen05.cu.
 #include <cstdio>
 #include <cstdlib>
 
@@ -36,21 +36,11 @@ namespace {
 
 constexpr int BW = 128;      // weight rows per CTA (TMEM lanes)
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 two epilogue warpgroups
 constexpr size_t kCounterBytes = 64 * 1024;
 constexpr int kStgPitch = BW * 2 + 16;           // staging row (one token, 128 features) + pad
 constexpr int kStgBytes = 2 * 32 * kStgPitch;    // double buffer of 32 tokens
 
-__device__ __forceinline__ float gelu_tanh_f(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * (x + k1 * x * x * x);
-  float t = 1.0f - 2.0f / (__expf(2.0f * u) + 1.0f);
-  return 0.5f * x * (1.0f + t);
-}
-__device__ __forceinline__ float gelu_erf_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
-}
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 struct SkinnyArgs {
   __nv_bfloat16* C;
@@ -64,13 +54,71 @@ struct SkinnyArgs {
   float* ws;        // [n_blk][split][m_pad][128] fp32 partials
   int* counters;    // [n_blocks]
   GemmEpilogue epi;
-  long long* dbg;   // profiling aid (VILA_B200_GEMM_DEBUG): 8 counters per CTA, or nullptr
+  int dbg_skip;     // profiling aid: 1 = skip the global stores, 2 = skip the transposed read-out
+  long long* dbg;   // profiling aid (VILA_B200_GEMM_DEBUG): 16 counters per CTA, or nullptr
 };
 
 __device__ __forceinline__ long long gtime_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+
+__device__ __forceinline__ void sts_bf16(uint32_t addr, float x) {
+  const __nv_bfloat16 h = __float2bfloat16(x);
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&h)) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "r"(addr));
+  return r;
+}
+// named barrier of one epilogue warpgroup (128 threads): ids 1 and 2
+__device__ __forceinline__ void epi_group_sync(int wg) {
+  asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+}
+
+// Transposed read-out of one staged 32-token chunk: kVpr 16-byte vectors per token row, all
+// trip counts compile-time so the shared loads / residual loads / stores of a thread are batched.
+template <int kVpr>
+__device__ __forceinline__ void readout(const uint8_t* buf, int epi_tid, int c, int nc0, int n_out,
+                                        const SkinnyArgs& a) {
+  constexpr int kIters = 32 * kVpr / 128;
+  const uint32_t base = smem_u32(buf);
+  uint4 o[kIters];
+#pragma unroll
+  for (int i = 0; i < kIters; ++i) {
+    const int q = epi_tid + i * 128;
+    o[i] = lds_v4(base + (q / kVpr) * kStgPitch + (q % kVpr) * 16);
+  }
+  if (a.epi.residual != nullptr) {
+    uint4 b[kIters];
+#pragma unroll
+    for (int i = 0; i < kIters; ++i) {
+      const int q = epi_tid + i * 128;
+      const int m = c * 32 + q / kVpr, nn = nc0 + (q % kVpr) * 8;
+      b[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (m < a.M && nn < n_out) {
+        const int rr = a.epi.res_row_mod > 0 ? (m % a.epi.res_row_mod) : m;
+        b[i] = ldg_v4(a.epi.residual + static_cast<size_t>(rr) * a.epi.ld_res + nn);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kIters; ++i) {
+      o[i].x = pack_bf16(bf_lo(o[i].x) + bf_lo(b[i].x), bf_hi(o[i].x) + bf_hi(b[i].x));
+      o[i].y = pack_bf16(bf_lo(o[i].y) + bf_lo(b[i].y), bf_hi(o[i].y) + bf_hi(b[i].y));
+      o[i].z = pack_bf16(bf_lo(o[i].z) + bf_lo(b[i].z), bf_hi(o[i].z) + bf_hi(b[i].z));
+      o[i].w = pack_bf16(bf_lo(o[i].w) + bf_lo(b[i].w), bf_hi(o[i].w) + bf_hi(b[i].w));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kIters; ++i) {
+    const int q = epi_tid + i * 128;
+    const int m = c * 32 + q / kVpr, nn = nc0 + (q % kVpr) * 8;
+    if (m < a.M && nn < n_out && a.dbg_skip != 1) stg_v4(a.C + static_cast<size_t>(m) * a.ldc + nn, o[i]);
+  }
 }
 
 template <bool kPair>
@@ -120,7 +168,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const uint32_t tmem_base = *tmem_ptr;
   griddep_launch_dependents();
 
-  long long* dbg = a.dbg ? a.dbg + 8 * blockIdx.x : nullptr;
+  long long* dbg = a.dbg ? a.dbg + 16 * blockIdx.x : nullptr;
   long long e0 = 0, e1 = 0;
   if (dbg && threadIdx.x == 0) {
     dbg[0] = gtime_ns();
@@ -210,13 +258,18 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       }
     }
   }
-  // ===================== epilogue warps (2..5) =====================
+  // ===================== epilogue: two warpgroups (warps 2..5 and 6..9) =====================
+  // Both groups cover all four TMEM lane quadrants; they take alternate 32-token chunks, each with
+  // its own staging tile and named barrier, so one group's TMEM read / activation math overlaps the
+  // other group's transposed read-out.
   const int quad = warp & 3;
-  const int epi_tid = threadIdx.x - 64;
+  const int wg = warp >= 6 ? 1 : 0;
+  const int epi_tid = static_cast<int>(threadIdx.x) - 64 - wg * 128;
   const int n_local = quad * 32 + lane;
   const int n = n_blk * BW + n_local;
   const bool n_ok = n < a.N;
   const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+  const int n_chunks = a.m_pad / 32;
   bool finalize = true;
   const float* slots = nullptr;
   float* dump = reinterpret_cast<float*>(smem);  // cluster split-K: [token][128] fp32 partial
@@ -234,7 +287,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       // (Peers PULL it after the cluster barrier: pushing into a peer would race with the peer's
       //  still-running main loop.)
 #pragma unroll 1
-      for (int c = 0; c < a.m_pad / 32; ++c) {
+      for (int c = wg; c < n_chunks; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
         tmem_ld_wait();
@@ -245,7 +298,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       const int my_unit = n_blk * a.splits + split;
       float* mine = a.ws + (static_cast<size_t>(my_unit) * a.m_pad) * BW + n_local;
 #pragma unroll 1
-      for (int c = 0; c < a.m_pad / 32; ++c) {
+      for (int c = wg; c < n_chunks; c += 2) {
         uint32_t r[32];
         if (kb1 > kb0) {
           tmem_ld_32x32b_x32(t_row + c * 32, r);
@@ -258,14 +311,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         for (int j = 0; j < 32; ++j) mine[static_cast<size_t>(c * 32 + j) * BW] = __uint_as_float(r[j]);
       }
       __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (epi_tid == 0) {
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      if (threadIdx.x == 64) {
         const int prev = atomicAdd(&a.counters[n_blk], 1);
         const int last = (prev == a.splits - 1) ? 1 : 0;
         if (last) a.counters[n_blk] = 0;
         *last_flag = last;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 3, 256;" ::: "memory");
       finalize = (*last_flag != 0);
       if (finalize) __threadfence();
       slots = a.ws + (static_cast<size_t>(n_blk) * a.splits * a.m_pad) * BW + n_local;
@@ -274,109 +327,99 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   // cluster split-K: the `splits` CTAs of one weight block form a cluster; once every partial is
   // parked, CTA r reduces the 32-token chunks c with c % splits == r straight out of its peers'
   // shared memory (DSMEM loads) in a fixed order — no workspace round trip, no counters, deterministic
+  const long long p1 = dbg ? clock64() : 0;
   if (a.cluster_k) cluster_sync_all();
+  const long long p2 = dbg ? clock64() : 0;
   if (warp >= 2 && finalize) {
     // ---- phase 2: bias / activation / transposition / store ----
     const bool swiglu = a.epi.swiglu != 0;
     const int act = a.epi.act;
     const bool dsmem = a.cluster_k && a.splits > 1;
-    {
-      const float bias = (a.epi.bias != nullptr && n_ok) ? __bfloat162float(a.epi.bias[n]) : 0.f;
-      // output row geometry of this CTA: features [nc0, nc0 + row_elems)
-      const int row_elems = swiglu ? BW / 2 : BW;
-      const int nc0 = swiglu ? (n_blk * BW) >> 1 : n_blk * BW;
-      const int n_out = swiglu ? a.N >> 1 : a.N;
-      const int vpr = row_elems / 8;  // 16-byte vectors per token row
-      const int c_first = dsmem ? split : 0, c_step = dsmem ? a.splits : 1;
-      int it = 0;
+    const float bias = (a.epi.bias != nullptr && n_ok) ? __bfloat162float(a.epi.bias[n]) : 0.f;
+    // output row geometry of this CTA: features [nc0, nc0 + 128 or 64)
+    const int nc0 = swiglu ? (n_blk * BW) >> 1 : n_blk * BW;
+    const int n_out = swiglu ? a.N >> 1 : a.N;
+    const int c_first = dsmem ? split : 0, c_step = dsmem ? a.splits : 1;
+    uint8_t* buf = stg + wg * (32 * kStgPitch);
 #pragma unroll 1
-      for (int c = c_first; c < a.m_pad / 32; c += c_step, ++it) {
-        if (c * 32 >= a.M) break;
-        float v[32];
-        if (dsmem) {
+    for (int c = c_first + wg * c_step; c < n_chunks; c += 2 * c_step) {
+      if (c * 32 >= a.M) break;
+      float v[32];
+      if (dsmem) {
+        // rank order 0..splits-1 (lowest k first); this CTA's own partial comes from local smem
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          const uint32_t off = smem_u32(dump) + static_cast<uint32_t>((c * 32) * BW + n_local) * 4u;
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        const uint32_t off = smem_u32(dump) + static_cast<uint32_t>((c * 32) * BW + n_local) * 4u;
 #pragma unroll 1
-          for (int s = 0; s < a.splits; ++s) {  // fixed order: rank 0 (lowest k) first
+        for (int s = 0; s < a.splits; ++s) {
+          if (s == split) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += dump[(c * 32 + j) * BW + n_local];
+          } else {
             const uint32_t base = mapa_u32(off, static_cast<uint32_t>(s));
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += ld_dsmem_f32(base + j * (BW * 4));
           }
-        } else if (a.splits > 1) {
+        }
+      } else if (a.splits > 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
 #pragma unroll 1
-          for (int s = 0; s < a.splits; ++s) {  // fixed order
-            const float* sp = slots + (static_cast<size_t>(s) * a.m_pad + c * 32) * BW;
+        for (int s = 0; s < a.splits; ++s) {  // fixed order
+          const float* sp = slots + (static_cast<size_t>(s) * a.m_pad + c * 32) * BW;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldcg(sp + static_cast<size_t>(j) * BW);
-          }
-        } else {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) v[j] += __ldcg(sp + static_cast<size_t>(j) * BW);
         }
-        uint8_t* buf = stg + (it & 1) * (32 * kStgPitch);
-        if (swiglu) {
-          // lanes (2i, 2i+1) hold (gate_i, up_i) of the interleaved weight rows
-          // The pair splits the 32 tokens: the even (gate) lane finishes tokens 0..15, the odd (up)
-          // lane tokens 16..31, so every lane does useful SiLU work and one shuffle serves two tokens.
-          const bool odd = (lane & 1) != 0;
-          __nv_bfloat16* dst =
-              reinterpret_cast<__nv_bfloat16*>(buf) + (n_local >> 1) + (odd ? 16 * (kStgPitch / 2) : 0);
+      } else {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, r);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a0 = bf16_round(v[j] + bias);       // this lane's row, token j
-            const float a1 = bf16_round(v[16 + j] + bias);  // this lane's row, token 16 + j
-            const float recv = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
-            const float gate = odd ? recv : a0;
-            const float up = odd ? a1 : recv;
-            dst[j * (kStgPitch / 2)] = __float2bfloat16(bf16_round(silu_f(gate)) * up);
-          }
-        } else {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf) + n_local;
-          if (act == ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dst[j * (kStgPitch / 2)] = __float2bfloat16(v[j] + bias);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float xb = bf16_round(v[j] + bias);
-              const float y = act == ACT_GELU_TANH ? gelu_tanh_f(xb)
-                                                   : (act == ACT_GELU_ERF ? gelu_erf_f(xb) : silu_f(xb));
-              dst[j * (kStgPitch / 2)] = __float2bfloat16(y);
-            }
-          }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        // transposed read-out: 16-byte vectors along the feature dimension
-        for (int q = epi_tid; q < 32 * vpr; q += 128) {
-          const int tok = q / vpr, seg = q - tok * vpr;
-          const int m = c * 32 + tok;
-          const int nn = nc0 + seg * 8;
-          if (m < a.M && nn < n_out) {
-            uint4 o = *reinterpret_cast<const uint4*>(buf + tok * kStgPitch + seg * 16);
-            if (a.epi.residual != nullptr) {
-              const int rr = a.epi.res_row_mod > 0 ? (m % a.epi.res_row_mod) : m;
-              const uint4 b = ldg_v4(a.epi.residual + static_cast<size_t>(rr) * a.epi.ld_res + nn);
-              o.x = pack_bf16(bf_lo(o.x) + bf_lo(b.x), bf_hi(o.x) + bf_hi(b.x));
-              o.y = pack_bf16(bf_lo(o.y) + bf_lo(b.y), bf_hi(o.y) + bf_hi(b.y));
-              o.z = pack_bf16(bf_lo(o.z) + bf_lo(b.z), bf_hi(o.z) + bf_hi(b.z));
-              o.w = pack_bf16(bf_lo(o.w) + bf_lo(b.w), bf_hi(o.w) + bf_hi(b.w));
-            }
-            stg_v4(a.C + static_cast<size_t>(m) * a.ldc + nn, o);
-          }
-        }
-        // (no second barrier: the next chunk writes the other staging buffer, and the barrier of
-        //  that iteration orders this read-out before the buffer is written again)
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       }
+      if (swiglu) {
+        // lanes (2i, 2i+1) hold (gate_i, up_i) of the interleaved weight rows.  The pair splits the
+        // 32 tokens: the even (gate) lane finishes tokens 0..15, the odd (up) lane tokens 16..31, so
+        // every lane does useful SiLU work and one shuffle serves two tokens.
+        const bool odd = (lane & 1) != 0;
+        const uint32_t dst = smem_u32(buf) + ((n_local >> 1) + (odd ? 16 * (kStgPitch / 2) : 0)) * 2;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a0 = bf16_round(v[j] + bias);       // this lane's row, token j
+          const float a1 = bf16_round(v[16 + j] + bias);  // this lane's row, token 16 + j
+          const float recv = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
+          const float gate = odd ? recv : a0;
+          const float up = odd ? a1 : recv;
+          sts_bf16(dst + j * kStgPitch, bf16_round(silu_f(gate)) * up);
+        }
+      } else {
+        const uint32_t dst = smem_u32(buf) + n_local * 2;
+        if (act == ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sts_bf16(dst + j * kStgPitch, v[j] + bias);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float xb = bf16_round(v[j] + bias);
+            const float y = act == ACT_GELU_TANH ? gelu_tanh_f(xb)
+                                                 : (act == ACT_GELU_ERF ? gelu_erf_f(xb) : silu_f(xb));
+            sts_bf16(dst + j * kStgPitch, y);
+          }
+        }
+      }
+      epi_group_sync(wg);
+      // transposed read-out: 16-byte vectors along the feature dimension
+      if (a.dbg_skip != 2) {
+        if (swiglu) readout<8>(buf, epi_tid, c, nc0, n_out, a);
+        else readout<16>(buf, epi_tid, c, nc0, n_out, a);
+      }
+      epi_group_sync(wg);  // the staging tile may be overwritten
     }
   }
 
   if (dbg && threadIdx.x == 64) {
+    dbg[8] = p1 - e1;            // phase 1 (partial leaves TMEM)
+    dbg[9] = p2 - p1;            // cluster barrier
     dbg[7] = e1 - e0;            // epilogue warps waiting for the accumulator
     dbg[5] = clock64() - e1;     // epilogue proper
   }
@@ -480,6 +523,8 @@ int launch_skinny(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int l
   a.ws = ws_ptr ? reinterpret_cast<float*>(static_cast<char*>(ws_ptr) + kCounterBytes) : nullptr;
   a.epi = epi;
   a.dbg = nullptr;
+  a.dbg_skip = 0;
+  if (const char* e = getenv("VILA_B200_GEMM_DEBUG_SKIP")) a.dbg_skip = atoi(e);
   if (const char* e = getenv("VILA_B200_GEMM_DEBUG")) {  // profiling aid: hex device pointer
     unsigned long long ptr = 0;
     if (sscanf(e, "%llx", &ptr) == 1) a.dbg = reinterpret_cast<long long*>(ptr);

@@ -34,8 +34,16 @@ constexpr int kNumThreads = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 
 // each CTA stages its own 128 rows of A and HALF of the W tile (BLOCK_N/2 rows); the tensor cores of
 // both SMs read both halves, so the bytes each SM pulls through its L2 port per MAC drop by 1/3
 // (128x256 tile: 48 KB -> 32 KB per k-block), which is what bounds the single-CTA kernel.
-template <int BLOCK_N, int kStages, bool kPair = false>
+//
+// kMode 2 (split-K pair): a 2-CTA cluster computes one 128 x BLOCK_N tile, each CTA half of the K
+// range with ordinary cta_group::1 MMAs; the two fp32 partials are exchanged through distributed
+// shared memory (each CTA parks the half of the columns it does NOT finalise, the peer pulls it),
+// so under-filled GEMMs (N = 1152 ViT out_proj / fc2: 72 tiles) use all 148 SMs.  One tile per pair.
+enum { kModeSingle = 0, kModePair = 1, kModeSplitK2 = 2 };
+
+template <int BLOCK_N, int kStages, int kMode = kModeSingle>
 struct GemmSmem {
+  static constexpr bool kPair = kMode == kModePair;
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBRows = kPair ? BLOCK_N / 2 : BLOCK_N;  // W rows staged by one CTA
   static constexpr int kBBytes = kBRows * BLOCK_K * 2;
@@ -44,17 +52,6 @@ struct GemmSmem {
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + align slack
 };
 
-__device__ __forceinline__ float gelu_tanh_f(float x) {
-  // gelu_pytorch_tanh: 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * (x + k1 * x * x * x);
-  float t = 1.0f - 2.0f / (__expf(2.0f * u) + 1.0f);
-  return 0.5f * x * (1.0f + t);
-}
-__device__ __forceinline__ float gelu_erf_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
-}
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float4 ld_cg_v4(const float* p) {
   float4 r;
@@ -107,12 +104,15 @@ struct Sched {
   }
 };
 
-template <int BLOCK_N, int kStages, bool kPair>
+template <int BLOCK_N, int kStages, int kMode>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_w, __nv_bfloat16* __restrict__ C,
                          int ldc, int M, int N, int K, GemmEpilogue epi) {
-  using S = GemmSmem<BLOCK_N, kStages, kPair>;
+  using S = GemmSmem<BLOCK_N, kStages, kMode>;
+  constexpr bool kPair = kMode == kModePair;
+  constexpr bool kSplit2 = kMode == kModeSplitK2;
+  constexpr bool kCluster = kPair || kSplit2;
   constexpr int TILE_M = kPair ? 2 * BLOCK_M : BLOCK_M;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -129,10 +129,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_m_blocks = (M + TILE_M - 1) / TILE_M;
-  const int stream_k = (!kPair && epi.split_k > 1) ? 1 : 0;
-  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
-  const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int n_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int stream_k = (!kCluster && epi.split_k > 1) ? 1 : 0;
+  const uint32_t rank = kCluster ? cluster_ctarank() : 0u;        // CTA within the pair
+  const uint32_t mrank = kPair ? rank : 0u;                       // pair mode: which half of the operands
+  const int worker = kCluster ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_workers = kCluster ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // split-K pair: this CTA's k-block range of every tile
+  const int nkb_all = (K + BLOCK_K - 1) / BLOCK_K;
+  const int sk_lo = (kSplit2 && rank == 1) ? (nkb_all + 1) / 2 : 0;
+  const int sk_hi = (kSplit2 && rank == 0) ? (nkb_all + 1) / 2 : nkb_all;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -154,7 +159,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     else tmem_alloc<2 * BLOCK_N>(tmem_ptr);
   }
   tc_fence_before();
-  if (kPair) cluster_sync_all();  // the peer's barriers exist before any remote signal
+  if (kCluster) cluster_sync_all();  // the peer's barriers exist before any remote signal
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
@@ -170,8 +175,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         else tma_load_2d(dst, tm, &full_bar[i], c0, c1);
       };
       constexpr uint32_t kTxBytes = S::kStageBytes * (kPair ? 2 : 1);
-      const int a_row_off = static_cast<int>(rank) * BLOCK_M;
-      const int w_row_off = static_cast<int>(rank) * S::kBRows;
+      const int a_row_off = static_cast<int>(mrank) * BLOCK_M;
+      const int w_row_off = static_cast<int>(mrank) * S::kBRows;
       int stage = 0;
       uint32_t phase = 0;
       int t, kb0, kb1;
@@ -181,11 +186,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int pt = 0, pkb0 = 0, pkb1 = 0;
       Sched peek = sch;
       const bool have_first = peek.next(pt, pkb0, pkb1);
+      if (kSplit2) {
+        pkb0 = sk_lo;
+        pkb1 = sk_hi;
+      }
       if (epi.static_w && have_first) {
         pre = min(kStages, pkb1 - pkb0);
         const int n_blk = pt / num_m_blocks;
         for (int i = 0; i < pre; ++i) {
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[i], kTxBytes);
+          if (mrank == 0) mbar_arrive_expect_tx(&full_bar[i], kTxBytes);
           load(smem_b + i * S::kBBytes, &tmap_w, i, (pkb0 + i) * BLOCK_K, n_blk * BLOCK_N + w_row_off);
         }
       }
@@ -196,13 +205,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       while (sch.next(t, kb0, kb1)) {
         const int m_blk = t % num_m_blocks;
         const int n_blk = t / num_m_blocks;
+        if (kSplit2) {
+          kb0 = sk_lo;
+          kb1 = sk_hi;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           if (first && (kb - kb0) < pre) {
             // W already in flight for this stage: only A is missing
             load(smem_a + stage * S::kABytes, &tmap_a, stage, kb * BLOCK_K, m_blk * TILE_M + a_row_off);
           } else {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], kTxBytes);
+            if (mrank == 0) mbar_arrive_expect_tx(&full_bar[stage], kTxBytes);
             load(smem_a + stage * S::kABytes, &tmap_a, stage, kb * BLOCK_K, m_blk * TILE_M + a_row_off);
             load(smem_b + stage * S::kBBytes, &tmap_w, stage, kb * BLOCK_K, n_blk * BLOCK_N + w_row_off);
           }
@@ -216,7 +229,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
-    if (lane == 0 && rank == 0) {
+    if (lane == 0 && mrank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
       Sched sch(M, N, K, BLOCK_N, stream_k, TILE_M, worker, n_workers);
       int stage = 0;
@@ -225,6 +238,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t aphase = 0;
       int t, kb0, kb1;
       while (sch.next(t, kb0, kb1)) {
+        if (kSplit2) {
+          kb0 = sk_lo;
+          kb1 = sk_hi;
+        }
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -272,10 +289,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_blk = t / num_m_blocks;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const int row = m_blk * TILE_M + static_cast<int>(rank) * BLOCK_M + quad * 32 + lane;
+      const int row = m_blk * TILE_M + static_cast<int>(mrank) * BLOCK_M + quad * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N;
-      const bool partial = (kb0 != 0) || (kb1 != sch.nkb);
+      const bool partial = !kSplit2 && ((kb0 != 0) || (kb1 != sch.nkb));
+      // split-K pair: park the column half the PEER finalises ([col/4][row] float4 -> conflict-free
+      // for the writer here and for the peer's DSMEM reads), then meet the peer at the cluster barrier
+      constexpr int kHalfChunks = BLOCK_N / 64;  // 32-column chunks per half
+      float4* xchg = reinterpret_cast<float4*>(smem_a);  // the pipeline stages are dead by now
+      if (kSplit2) {
+        const int c_peer = static_cast<int>(1u - rank) * kHalfChunks;
+#pragma unroll 1
+        for (int c = 0; c < kHalfChunks; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + (c_peer + c) * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            xchg[(c * 8 + g) * BLOCK_M + quad * 32 + lane] =
+                make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                            __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+        }
+        cluster_sync_all();  // (warps 0/1 execute the matching barrier after their loops)
+      }
+      const uint32_t xchg_peer = kSplit2 ? mapa_u32(smem_u32(xchg), 1u - rank) : 0u;
       bool finalize = true;       // apply the epilogue and write C
       bool from_ws = false;       // accumulator comes from the fp32 workspace
       int n_slots = 0;
@@ -332,8 +369,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const int rr = epi.res_row_mod > 0 ? (row % epi.res_row_mod) : row;
           res_row = epi.residual + static_cast<size_t>(rr) * epi.ld_res;
         }
+        const int c_lo = kSplit2 ? static_cast<int>(rank) * kHalfChunks : 0;
+        const int c_hi = kSplit2 ? c_lo + kHalfChunks : BLOCK_N / 32;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           float v[32];
           const int n0 = n_blk * BLOCK_N + c * 32;
           if (!from_ws) {
@@ -342,6 +381,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (kSplit2) {
+              // + the peer's partial of the same columns (two operands: order-independent)
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 q = ld_dsmem_v4f(
+                    xchg_peer + static_cast<uint32_t>(((c - c_lo) * 8 + g) * BLOCK_M + quad * 32 + lane) * 16u);
+                v[4 * g + 0] += q.x; v[4 * g + 1] += q.y; v[4 * g + 2] += q.z; v[4 * g + 3] += q.w;
+              }
+            }
           } else {
             if (n0 >= N) continue;
 #pragma unroll
@@ -446,7 +494,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 
   tc_fence_before();
-  if (kPair) cluster_sync_all();  // the leader's MMAs read the peer's shared memory until the end
+  if (kSplit2 && warp < 2) cluster_sync_all();  // matches the epilogue warps' exchange barrier
+  // pair: the leader's MMAs read the peer's shared memory until the end; split-K pair: the peer
+  // pulls this CTA's parked partial
+  if (kCluster) cluster_sync_all();
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -463,16 +514,17 @@ struct Workspace {
 Workspace g_ws;
 constexpr size_t kCounterBytes = 64 * 1024;  // 16384 tile counters
 
-template <int BLOCK_N, int kStages, bool kPair = false>
+template <int BLOCK_N, int kStages, int kMode = kModeSingle>
 int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
                 int ldc, int M, int N, int K, GemmEpilogue epi, int force_stream_k,
                 cudaStream_t stream) {
-  using S = GemmSmem<BLOCK_N, kStages, kPair>;
+  using S = GemmSmem<BLOCK_N, kStages, kMode>;
+  constexpr bool kPair = kMode == kModePair;
   constexpr int TILE_M = kPair ? 2 * BLOCK_M : BLOCK_M;
   CUtensorMap ta, tw;
   if (make_tmap_2d_bf16(&ta, A, M, K, lda, BLOCK_M, BLOCK_K, 128)) return 1;
   if (make_tmap_2d_bf16(&tw, W, N, K, ldw, S::kBRows, BLOCK_K, 128)) return 1;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, kStages, kPair>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, kStages, kMode>;
   static bool attr_set = false;
   if (!attr_set) {
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -480,6 +532,17 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
   }
   const int sms = num_sms();
   const int tiles = ((M + TILE_M - 1) / TILE_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  if (kMode == kModeSplitK2) {
+    // one 128 x BLOCK_N tile per CTA pair, half of K each
+    if (tiles > sms / 2 || (K + BLOCK_K - 1) / BLOCK_K < 2) {
+      set_last_error("gemm: split-K pairs need <= %d tiles and >= 2 k-blocks (tiles=%d)", sms / 2, tiles);
+      return 1;
+    }
+    epi.split_k = 1;
+    VB_CUDA(launch_pdl_cluster(kern, dim3(2 * tiles), dim3(kNumThreads), S::kTotal, stream,
+                               dim3(2, 1, 1), ta, tw, C, ldc, M, N, K, epi));
+    return 0;
+  }
   if (kPair) {
     // data-parallel over 256 x BLOCK_N tiles, one tile at a time per CTA pair
     const int pairs = tiles < sms / 2 ? tiles : sms / 2;
@@ -572,7 +635,7 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
   const long pair_tiles = static_cast<long>((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + 255) / 256);
   const long m_pad_pair = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * (2L * BLOCK_M), m_pad_single = static_cast<long>(mb) * BLOCK_M;
   if (pair_tiles * 20 >= 17L * (sms / 2) && m_pad_pair * 8 <= m_pad_single * 9)  // no extra row padding
-    return launch_gemm<256, 6, true>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
+    return launch_gemm<256, 6, kModePair>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
   const long tiles256 = static_cast<long>(mb) * ((N + 255) / 256);
   if (tiles256 * 10 >= 7L * sms)
     return launch_gemm<256, 4>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
@@ -581,13 +644,15 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
 }
 
 // test hook: force a tile configuration (block_n in {64,128,256}; +1000 forces stream-K, +2000 off;
-// 3000 / 3001: swap-AB skinny kernel, single CTA / CTA pair; 4128 / 4256: CTA-pair 256 x BLOCK_N tiles)
+// 3000 / 3001: swap-AB skinny kernel, single CTA / CTA pair; 4128 / 4256: CTA-pair 256 x BLOCK_N
+// tiles; 5128: split-K CTA pairs on 128 x 128 tiles)
 int gemm_bf16_cfg(int block_n, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw,
                   __nv_bfloat16* C, int ldc, int M, int N, int K, const GemmEpilogue& epi,
                   cudaStream_t stream) {
   if (check_args(A, lda, W, ldw, C, ldc, M, N, K, epi)) return 1;
-  if (block_n == 4256) return launch_gemm<256, 6, true>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
-  if (block_n == 4128) return launch_gemm<128, 8, true>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
+  if (block_n == 4256) return launch_gemm<256, 6, kModePair>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
+  if (block_n == 4128) return launch_gemm<128, 8, kModePair>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
+  if (block_n == 5128) return launch_gemm<128, 6, kModeSplitK2>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
   if (block_n == 3000 || block_n == 3001) {
     const int rc = gemm_skinny_bf16(A, lda, W, ldw, C, ldc, M, N, K, epi, block_n - 3000, stream);
     if (rc < 0) set_last_error("gemm_bf16_cfg: skinny kernel does not handle M=%d", M);

@@ -24,7 +24,6 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxStages = 6;
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc) {
   acc = fmaf(bf_lo(w.x), bf_lo(x.x), acc);
