@@ -37,8 +37,8 @@ struct FmhaCfg {
   static constexpr int kSwizzleBytes = CW * 2;
   static constexpr int kSBO = 8 * CW * 2;  // 8-row group pitch
   static constexpr int kPBytes = BQ * BKV * 2;
-  static constexpr int kNumBars = 18;
-  static constexpr int kSmem = kTileBytes * 5 + kPBytes + kNumBars * 8 + 16 + 1024;
+  static constexpr int kNumBars = 20;
+  static constexpr int kSmem = kTileBytes * 5 + 2 * kPBytes + kNumBars * 8 + 16 + 1024;  // P double-buffered
   static constexpr int kTmemO = 256;  // S0 @ 0, S1 @ 128, O @ 256
 };
 
@@ -69,7 +69,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* k_s = q_s + C::kTileBytes;       // 2 stages
   uint8_t* v_s = k_s + 2 * C::kTileBytes;   // 2 stages
   uint8_t* p_s = v_s + 2 * C::kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + C::kPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * C::kPBytes);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;   // [2]
   uint64_t* k_empty = bars + 3;  // [2]
@@ -77,11 +77,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* v_empty = bars + 7;  // [2]
   uint64_t* s_full = bars + 9;   // [2]
   uint64_t* s_free = bars + 11;  // [2]
-  uint64_t* p_full = bars + 13;
-  uint64_t* p_free = bars + 14;
-  uint64_t* o_full = bars + 15;
-  uint64_t* o_free = bars + 16;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* p_full = bars + 13;  // [2]
+  uint64_t* p_free = bars + 15;  // [2]
+  uint64_t* o_full = bars + 17;
+  uint64_t* o_free = bars + 18;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,9 +107,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&p_free[i], 1);
     }
-    mbar_init(p_full, 128);
-    mbar_init(p_free, 1);
     mbar_init(o_full, 1);
     mbar_init(o_free, 128);
     fence_barrier_init();
@@ -188,15 +188,15 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int j = 0; j < nblk; ++j) {
         if (j + 1 < nblk) issue_s(j + 1);
         const int s = j & 1;
-        mbar_wait(p_full, j & 1);
+        mbar_wait(&p_full[s], (j >> 1) & 1);
         mbar_wait(&v_full[s], (j >> 1) & 1);
-        mbar_wait(o_free, (j & 1) ^ 1);
+        mbar_wait(o_free, (j & 1) ^ 1);  // O_{j-1} has been read out of TMEM
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           // A = P: two 64-column SW128 chunks of [128][64]; step 16 columns = 32 bytes
-          const uint64_t ad = make_smem_desc(smem_u32(p_s + (k >> 2) * (BQ * 128)) + (k & 3) * 32, 16,
-                                             1024, kLayoutSW128);
+          const uint64_t ad = make_smem_desc(
+              smem_u32(p_s + s * C::kPBytes + (k >> 2) * (BQ * 128)) + (k & 3) * 32, 16, 1024, kLayoutSW128);
           // B = V (MN-major): N spans the d-chunks (LBO = chunk pitch), K = 16 token rows per MMA
           const uint64_t bd =
               make_smem_desc(smem_u32(v_s + s * C::kTileBytes) + k * 16 * (CW * 2),
@@ -204,7 +204,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           umma_f16(tmem_base + C::kTmemO, ad, bd, idesc_o, k != 0 ? 1u : 0u);
         }
         umma_commit(&v_empty[s]);
-        umma_commit(p_free);
+        umma_commit(&p_free[s]);
         umma_commit(o_full);
       }
     }
@@ -247,8 +247,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = ex2(m - m_use);  // m == -inf -> 0
 
-      // pass 2: P = exp2(S*scale - m) -> bf16 -> swizzled smem
-      mbar_wait(p_free, (j & 1) ^ 1);
+      // pass 2: P = exp2(S*scale - m) -> bf16 -> swizzled smem (double-buffered: P_j is written
+      // while the tensor core is still reading P_{j-1})
+      mbar_wait(&p_free[s], ((j >> 1) & 1) ^ 1);
       float rowsum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < BKV / 32; ++c) {
@@ -263,7 +264,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           p[i] = e;
           rowsum += e;
         }
-        uint8_t* prow = p_s + (c >> 1) * (BQ * 128) + row * 128;
+        uint8_t* prow = p_s + s * C::kPBytes + (c >> 1) * (BQ * 128) + row * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int piece = (c & 1) * 4 + g;
@@ -278,12 +279,31 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       l = l * alpha + rowsum;
       m = m_new;
       fence_proxy_async_smem();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[s]);
       tc_fence_before();
       mbar_arrive(&s_free[s]);
 
-      // accumulate O_j
-      mbar_wait(o_full, j & 1);
+      // Deferred accumulation: P_{j-1} V_{j-1} ran on the tensor core while this tile's softmax was
+      // computed; fold it in now.  o_acc holds acc_j - P_j V_j = (o_acc + P_{j-1} V_{j-1}) * alpha_j.
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+        const uint32_t o_addr = tmem_base + lane_addr + C::kTmemO;
+#pragma unroll
+        for (int c = 0; c < DP / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(o_addr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(r[i])) * alpha;
+        }
+        tc_fence_before();
+        mbar_arrive(o_free);
+      }
+    }
+    if (nblk > 0) {  // the last tile's P V
+      mbar_wait(o_full, (nblk - 1) & 1);
       tc_fence_after();
       const uint32_t o_addr = tmem_base + lane_addr + C::kTmemO;
 #pragma unroll
@@ -292,10 +312,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_32x32b_x32(o_addr + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(r[i]);
       }
-      tc_fence_before();
-      mbar_arrive(o_free);
     }
 
     if (q_idx < a.Sq) {
@@ -382,13 +400,18 @@ int fmha_prefill(const FmhaParams& p, cudaStream_t stream) {
            "fmha: strides must be multiples of 8 elements (16 bytes)");
   VB_CHECK(!p.causal || p.Sk >= p.Sq, "fmha: causal needs Sk >= Sq");
   {
-    // v2 (two query tiles per CTA, ping-pong softmax warpgroups) whenever there are >= 2 tiles
-    static int force_v1 = -1;
-    if (force_v1 < 0) {
+    // v2 (two query tiles per CTA, ping-pong softmax warpgroups) once its 256-row CTAs fill the
+    // machine; below that the one-tile-per-CTA kernel has twice the CTAs and the shorter critical
+    // path (1 image, 1024 x 16 heads: 22.5 vs 28.2 us; 64 images: 1105 vs 729 us).
+    // VILA_B200_FMHA_V1=1 / =0 forces v1 / v2 (test hook).
+    static int force = -2;
+    if (force == -2) {
       const char* e = getenv("VILA_B200_FMHA_V1");
-      force_v1 = (e && e[0] == '1') ? 1 : 0;
+      force = e ? (e[0] == '1' ? 1 : 0) : -1;
     }
-    if (!force_v1 && p.Sq > 128) {
+    const long v2_ctas = static_cast<long>((p.Sq + 255) / 256) * p.Hq * p.B;
+    const bool use_v2 = force == 0 ? p.Sq > 128 : (force == 1 ? false : (p.Sq > 128 && v2_ctas >= num_sms()));
+    if (use_v2) {
       const int rc = fmha_prefill_v2(p, stream);
       if (rc >= 0) return rc;
     }

@@ -624,12 +624,17 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
   // Few tokens (short-prompt prefill, projector): the weights dominate the traffic -> swap-AB kernel
   // (every weight byte enters an SM once; cluster split-K fills the machine).  B200, M = 279:
   // down-proj 52 vs 90 us, gate/up 83 vs 86, qkv/o 21-23 vs 22 (profiles/r01_gemm_configs.md)
+  const int sms = num_sms();
+  const int mb = (M + BLOCK_M - 1) / BLOCK_M;
+  // Long-K GEMMs with at most one 128x128 tile per SM pair (ViT fc2: 72 tiles, K = 4304; projector):
+  // split K over a CTA pair with a DSMEM exchange -> all SMs stream operands (fc2 16.9 vs 24.7 us).
+  const long tiles128 = static_cast<long>(mb) * ((N + 127) / 128);
+  const bool split2 = tiles128 <= sms / 2 && K >= 2048 && M * 10 >= mb * BLOCK_M * 9;
+  if (split2) return launch_gemm<128, 6, kModeSplitK2>(A, lda, W, ldw, C, ldc, M, N, K, epi, -1, stream);
   if (M <= 384) {
     const int rc = gemm_skinny_bf16(A, lda, W, ldw, C, ldc, M, N, K, epi, 0, stream);
     if (rc >= 0) return rc;
   }
-  const int sms = num_sms();
-  const int mb = (M + BLOCK_M - 1) / BLOCK_M;
   // CTA pairs (256 x 256 tiles, cta_group::2) once they fill ~85 % of the SM pairs: fewer bytes per
   // MAC through each SM's L2 port and shared memory (8192^3: 752 vs 859 us; 2048x37888x3584: 355 vs 396)
   const long pair_tiles = static_cast<long>((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + 255) / 256);
