@@ -1,7 +1,7 @@
 """GPU: BASELINE.json's full-size configurations through size-independent properties (the CPU oracle
 cannot finish these sizes in seconds):
   #2 NVILA-8B request        greedy decode is bit-reproducible; KV-cached decode == re-prefill
-  #3 NVILA-Video-8B 64 frames batched vision encode == per-frame encode (bit-exact);
+  #3 NVILA-Video-8B 64 frames batched vision encode == per-frame encode (bf16 noise; each bit-reproducible);
                              chunked prefill (S = 16.4K in two chunks) == single prefill
   #4 dynamic-S2 35 tiles     encode_images shape / finiteness / reproducibility, single-tile path
 One 8B-scale random-init model is shared by the module (~20 s to build on a B200)."""
@@ -59,9 +59,14 @@ def test_cfg3_video_batch_invariance_and_chunked_prefill(cuda):
     frames = torch.randn(64, 3, 448, 448, device="cuda", generator=g).to(torch.bfloat16)
     feats = model.encode_images(frames).clone()
     assert feats.shape == (64, 256, cfg.hidden_size) and torch.isfinite(feats.float()).all()
-    for i in (0, 37, 63):  # batched encode == single-frame encode, bit for bit
+    # batched encode vs single-frame encode: the kernels are chosen by problem size (one frame:
+    # split-K CTA pairs + one-tile FMHA; 64 frames: 256x256 pair tiles + two-tile FMHA), so the
+    # fp32 summation order differs -> equal to bf16 noise, and each path is bit-reproducible
+    for i in (0, 37, 63):
         one = model.encode_images(frames[i:i + 1]).clone()
-        assert torch.equal(one[0], feats[i]), i
+        assert rel(one[0], feats[i]) < 3e-2, (i, rel(one[0], feats[i]))
+        assert torch.equal(one, model.encode_images(frames[i:i + 1]))
+    assert torch.equal(feats, model.encode_images(frames))
     enc = model.encoders["video"]([frames], {})[0]
     assert enc.shape == (64 * 257, cfg.hidden_size)
     llm = model.llm
