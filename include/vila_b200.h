@@ -67,7 +67,11 @@ int vila_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int vila_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const void* bias,
                 const void* residual, int64_t ld_res, int res_row_mod, void* out, int64_t ldo,
                 int M, int N, int K, int act, int flags, void* stream);
-/* test hook: same, forcing the N tile (64 / 128 / 256) */
+/* test hook: same, forcing the kernel configuration instead of the size heuristic:
+ *   64 / 128 / 256   single-CTA tiles 128 x block_n (+1000: deterministic stream-K, +2000: stream-K off)
+ *   4128 / 4256      CTA-pair tiles 256 x {128,256} (tcgen05 cta_group::2)
+ *   5128             split-K CTA pairs on 128 x 128 tiles (needs <= #SM/2 tiles, K > 64)
+ *   3000 / 3001      swap-AB skinny kernel (M <= 512), one CTA / CTA pair per weight block */
 int vila_linear_cfg(int block_n, const void* x, int64_t ldx, const void* w, int64_t ldw,
                     const void* bias, const void* residual, int64_t ld_res, int res_row_mod,
                     void* out, int64_t ldo, int M, int N, int K, int act, int flags, void* stream);
