@@ -135,6 +135,21 @@ int vila_embed_splice(const void* table, const void* media, const int32_t* src, 
 int vila_rope_kv_append(void* qkv, const int32_t* positions, int S, int Hq, int Hkv, int D,
                         const float* inv_freq, void* k_pool, void* v_pool,
                         const int32_t* page_table, int cache_pos0, void* stream);
+/* Fused q/k/v projection for a short prefill chunk (M <= 384 tokens, head_dim 128):
+ * qkv = x @ w^T + bias; RoPE on the q and k heads; q heads -> qkv_out[:, :Hq*128]; k / v heads ->
+ * the paged pools (k_pool NULL: they stay in qkv_out) — vila_linear followed by vila_rope_kv_append
+ * in ONE kernel, bit-identical to the two calls (rope_table: vila_rope_table of the chunk's positions).  Replaces Qwen2Attention's q_proj/k_proj/v_proj +
+ * apply_rotary_pos_emb + past_key_value.update (modeling_qwen2.py:223-226,99-160,262-266 of the
+ * in-tree copy).  Returns 3 (and sets vila_last_error) when the shape is not covered: the caller
+ * then issues the two separate calls. */
+int vila_linear_qkv_rope(const void* x, int64_t ldx, const void* w, int64_t ldw, const void* bias,
+                         void* qkv_out, int64_t ldo, int M, int K, int Hq, int Hkv, int D,
+                         const void* rope_table, void* k_pool, void* v_pool,
+                         const int32_t* page_table, int cache_pos0, int flags, void* stream);
+/* cos / sin table of Qwen2RotaryEmbedding.forward (modeling_qwen2.py:99-143) for one request,
+ * computed once and shared by all layers: table [S, D] bf16 = cos(pos*inv_freq[0..D/2)) | sin(...). */
+int vila_rope_table(const int32_t* positions, int S, int D, const float* inv_freq, void* table,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * decode (one token): weight-streaming GEMV with fused RMSNorm prologue and bias / residual /

@@ -111,6 +111,40 @@ def test_linear_streamk_epilogues_and_workspace_is_clean(cuda):
     assert rel_err(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("M", [1, 33, 279, 384])
+def test_linear_qkv_rope_fused_equals_two_kernels(cuda, M):
+    """q/k/v projection with RoPE + paged KV append fused into the GEMM epilogue must be bit-identical
+    to vila_linear followed by vila_rope_kv_append (same rounding points), including the pool scatter
+    through a permuted page table and a non-zero cache offset."""
+    ops = _ops()
+    Hq, Hkv, D, K = 6, 2, 128, 512
+    N = (Hq + 2 * Hkv) * D
+    g = torch.Generator(device="cuda").manual_seed(100 + M)
+    x = bf(torch.randn(M, K, device=cuda, generator=g))
+    w = bf(torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K))
+    b = bf(torch.randn(N, device=cuda, generator=g))
+    p0 = 77
+    pos = torch.arange(p0, p0 + M, dtype=torch.int32, device=cuda) * 3 + 5
+    inv_freq = (1.0 / (1e6 ** (torch.arange(0, D, 2, dtype=torch.float32) / D))).to(cuda)
+    n_pages = (p0 + M + 127) // 128 + 2
+    table = torch.randperm(n_pages, generator=torch.Generator().manual_seed(1)).to(torch.int32).to(cuda)
+    pools = [torch.zeros(n_pages, 128, Hkv, D, dtype=torch.bfloat16, device=cuda) for _ in range(4)]
+    ref = ops.linear(x, w, b, block_n=3000)  # the same swap-AB GEMM, plain epilogue
+    ops.rope_kv_append(ref, pos, Hq, Hkv, D, inv_freq, pools[0], pools[1], table, p0)
+    tab = ops.rope_table(pos, D, inv_freq)
+    got = ops.linear_qkv_rope(x, w, b, tab, Hq, Hkv, D, pools[2], pools[3], table, p0)
+    assert got is not None
+    assert torch.equal(got[:, :Hq * D], ref[:, :Hq * D])
+    assert torch.equal(pools[2], pools[0]) and torch.equal(pools[3], pools[1])
+    # without pools the rotated k and the plain v stay in the output buffer
+    ref2 = ops.linear(x, w, b, block_n=3000)
+    ops.rope_kv_append(ref2, pos, Hq, Hkv, D, inv_freq)
+    assert torch.equal(ops.linear_qkv_rope(x, w, b, tab, Hq, Hkv, D), ref2)
+    # not covered -> None (the caller falls back to the two kernels)
+    assert ops.linear_qkv_rope(torch.zeros(400, K, dtype=torch.bfloat16, device=cuda), w, b,
+                               torch.zeros(400, D, dtype=torch.bfloat16, device=cuda), Hq, Hkv, D) is None
+
+
 def test_linear_chain_under_pdl(cuda):
     """Back-to-back dependent kernels (programmatic dependent launch): every consumer must wait for
     its producer; weights flagged static may be fetched early."""

@@ -163,6 +163,40 @@ int vila_rope_kv_append(void* qkv, const int32_t* positions, int S, int Hq, int 
                             page_table, cache_pos0, st(stream));
 }
 
+int vila_linear_qkv_rope(const void* x, int64_t ldx, const void* w, int64_t ldw, const void* bias,
+                         void* qkv_out, int64_t ldo, int M, int K, int Hq, int Hkv, int D,
+                         const void* rope_table, void* k_pool, void* v_pool,
+                         const int32_t* page_table, int cache_pos0, int flags, void* stream) {
+  VB_REQUIRE_DEVICE();
+  if (D != 128 || M > 384 || rope_table == nullptr) {
+    vb::set_last_error("vila_linear_qkv_rope: needs head_dim 128 and M <= 384 (D=%d, M=%d)", D, M);
+    return 3;
+  }
+  vb::GemmEpilogue e;
+  e.bias = cb(bias);
+  e.static_w = (flags & VILA_FLAG_STATIC_W) ? 1 : 0;
+  e.rope_table = cb(rope_table);
+  e.k_pool = mb(k_pool);
+  e.v_pool = mb(v_pool);
+  e.page_table = page_table;
+  e.cache_pos0 = cache_pos0;
+  e.rope_hq = Hq;
+  e.rope_hkv = Hkv;
+  const int rc = vb::gemm_qkv_rope_bf16(cb(x), (int)ldx, cb(w), (int)ldw, mb(qkv_out), (int)ldo, M,
+                                        (Hq + 2 * Hkv) * D, K, e, st(stream));
+  if (rc < 0) {
+    vb::set_last_error("vila_linear_qkv_rope: shape not covered (M=%d)", M);
+    return 3;
+  }
+  return rc;
+}
+
+int vila_rope_table(const int32_t* positions, int S, int D, const float* inv_freq, void* table,
+                    void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::rope_table(positions, S, D, inv_freq, mb(table), st(stream));
+}
+
 int vila_gemv(const vila_gemv_params* p, void* stream) {
   VB_REQUIRE_DEVICE();
   vb::GemvParams g;

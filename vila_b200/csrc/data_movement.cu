@@ -252,7 +252,37 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* _
   }
 }
 
+// cos / sin of HF Qwen2RotaryEmbedding for a request, computed once and shared by all layers and
+// heads: table[s] = bf16(cos(pos[s] * inv_freq[i])) for i < D/2, then bf16(sin(...)).
+__global__ void rope_table_kernel(const int32_t* __restrict__ pos, int S, int half,
+                                  const float* __restrict__ inv_freq_tab,
+                                  __nv_bfloat16* __restrict__ table) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const long total = (long)S * half;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const int i = idx % half;
+    const int s = idx / half;
+    const float ang = (float)pos[s] * inv_freq_tab[i];
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    table[(long)s * 2 * half + i] = __float2bfloat16(cs);
+    table[(long)s * 2 * half + half + i] = __float2bfloat16(sn);
+  }
+}
+
 }  // namespace
+
+int rope_table(const int32_t* positions, int S, int D, const float* inv_freq, __nv_bfloat16* table,
+               cudaStream_t stream) {
+  VB_CHECK(D % 2 == 0, "rope_table: head dim must be even");
+  if (S == 0) return 0;
+  const long total = (long)S * (D / 2);
+  VB_CUDA(launch_pdl(rope_table_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, positions, S, D / 2,
+                     inv_freq, table));
+  return 0;
+}
 
 int im2col_patch14(const __nv_bfloat16* pixels, __nv_bfloat16* out, int B, int C, int H, int W,
                    int patch, int k_pad, cudaStream_t stream) {

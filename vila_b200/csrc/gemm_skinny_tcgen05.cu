@@ -121,6 +121,62 @@ __device__ __forceinline__ void readout(const uint8_t* buf, int epi_tid, int c, 
   }
 }
 
+// Read-out of one staged 32-token chunk of ONE attention head (this CTA's 128 features) for the fused
+// q/k/v projection: HF apply_rotary_pos_emb (rotate-half; cos/sin from the per-request bf16 table, every
+// product rounded to bf16 before the sum — exactly rope_kv_kernel in data_movement.cu) on q and k
+// heads, then q -> C, k / v -> the paged KV pool (DynamicCache.update as a scatter).
+__device__ __forceinline__ void readout_rope(const uint8_t* buf, int epi_tid, int c, int head,
+                                             const SkinnyArgs& a) {
+  const uint32_t base = smem_u32(buf);
+  const GemmEpilogue& e = a.epi;
+  const bool is_q = head < e.rope_hq;
+  const bool is_v = head >= e.rope_hq + e.rope_hkv;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int q = epi_tid + i * 128;  // 32 tokens x 8 segments of 8 rotation pairs
+    const int tok = q >> 3, seg = q & 7;
+    const int m = c * 32 + tok;
+    if (m >= a.M) continue;
+    uint4 lo = lds_v4(base + tok * kStgPitch + seg * 16);         // features [8 seg, 8 seg + 8)
+    uint4 hi = lds_v4(base + tok * kStgPitch + 128 + seg * 16);   // features 64 + [8 seg, 8 seg + 8)
+    if (!is_v) {
+      const uint4 cv = ldg_v4(e.rope_table + static_cast<size_t>(m) * 128 + seg * 8);
+      const uint4 sv = ldg_v4(e.rope_table + static_cast<size_t>(m) * 128 + 64 + seg * 8);
+      uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
+      uint32_t* hw = reinterpret_cast<uint32_t*>(&hi);
+      const uint32_t* cw = reinterpret_cast<const uint32_t*>(&cv);
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sv);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        float y0[2], y1[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const float x0 = hf ? bf_hi(lw[w]) : bf_lo(lw[w]);
+          const float x1 = hf ? bf_hi(hw[w]) : bf_lo(hw[w]);
+          const float cs = hf ? bf_hi(cw[w]) : bf_lo(cw[w]);
+          const float sn = hf ? bf_hi(sw[w]) : bf_lo(sw[w]);
+          y0[hf] = bf16_round(x0 * cs) + bf16_round(-x1 * sn);
+          y1[hf] = bf16_round(x1 * cs) + bf16_round(x0 * sn);
+        }
+        lw[w] = pack_bf16(y0[0], y0[1]);
+        hw[w] = pack_bf16(y1[0], y1[1]);
+      }
+    }
+    __nv_bfloat16* dst;
+    if (is_q || e.k_pool == nullptr) {
+      dst = a.C + static_cast<size_t>(m) * a.ldc + head * 128;
+    } else {
+      const int cpos = e.cache_pos0 + m;
+      const int page = e.page_table[cpos >> 7];
+      const int hk = (head - e.rope_hq) % e.rope_hkv;
+      dst = (is_v ? e.v_pool : e.k_pool) +
+            ((static_cast<size_t>(page) * 128 + (cpos & 127)) * e.rope_hkv + hk) * 128;
+    }
+    stg_v4(dst + seg * 8, lo);
+    stg_v4(dst + 64 + seg * 8, hi);
+  }
+}
+
 template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
@@ -410,7 +466,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       epi_group_sync(wg);
       // transposed read-out: 16-byte vectors along the feature dimension
       if (a.dbg_skip != 2) {
-        if (swiglu) readout<8>(buf, epi_tid, c, nc0, n_out, a);
+        if (a.epi.rope_table != nullptr) readout_rope(buf, epi_tid, c, n_blk, a);
+        else if (swiglu) readout<8>(buf, epi_tid, c, nc0, n_out, a);
         else readout<16>(buf, epi_tid, c, nc0, n_out, a);
       }
       epi_group_sync(wg);  // the staging tile may be overwritten
@@ -546,6 +603,13 @@ int launch_skinny(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int l
 int gemm_skinny_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
                      int ldc, int M, int N, int K, const GemmEpilogue& epi, int pair, cudaStream_t stream) {
   if (M > 512 || M < 1) return -1;
+  if (epi.rope_table != nullptr) {
+    VB_CHECK(N == (epi.rope_hq + 2 * epi.rope_hkv) * 128 && !epi.swiglu &&
+                 epi.act == ACT_NONE && epi.residual == nullptr &&
+                 (epi.k_pool == nullptr || (epi.v_pool != nullptr && epi.page_table != nullptr)),
+             "gemm_skinny: the fused q/k/v RoPE epilogue needs head_dim 128, N = (Hq + 2 Hkv) * 128 and "
+             "no other epilogue");
+  }
   return pair ? launch_skinny<true>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream)
               : launch_skinny<false>(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
 }

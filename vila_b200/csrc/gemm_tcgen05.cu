@@ -600,6 +600,15 @@ int check_args(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw,
 
 }  // namespace
 
+// q/k/v projection with RoPE + KV-cache append fused into the epilogue (swap-AB kernel, M <= 384,
+// head_dim 128).  Returns -1 when the shape is not covered (caller: plain GEMM + rope_kv_append).
+int gemm_qkv_rope_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
+                       int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
+  if (check_args(A, lda, W, ldw, C, ldc, M, N, K, epi)) return 1;
+  if (M > 384) return -1;
+  return gemm_skinny_bf16(A, lda, W, ldw, C, ldc, M, N, K, epi, 0, stream);
+}
+
 void get_workspace(void** ptr, size_t* bytes) {
   *ptr = g_ws.ptr;
   *bytes = g_ws.bytes;
@@ -616,6 +625,7 @@ int set_workspace(void* ptr, size_t bytes) {
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
               int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream) {
   if (check_args(A, lda, W, ldw, C, ldc, M, N, K, epi)) return 1;
+  VB_CHECK(epi.rope_table == nullptr, "gemm: the fused RoPE epilogue is only available through gemm_qkv_rope_bf16");
   // Tile-shape heuristic. N=256 tiles keep the MMA (not shared-memory bandwidth) the limiter when
   // there is enough work; N=128 otherwise; stream-K (inside launch_gemm) fixes SM under-fill.
   // Measured on B200 (tools/bench_gemm.py): 128x256 tiles win as soon as they fill ~70 % of the

@@ -22,6 +22,15 @@ struct GemmEpilogue {
   float* splitk_ws = nullptr;
   int* splitk_counters = nullptr;
   int split_k = 1;
+  // fused q/k/v projection epilogue (skinny kernel only, head_dim == 128): RoPE on the q and k heads
+  // and the KV-cache append, i.e. what rope_kv_append() does as a separate kernel.  Enabled when
+  // rope_table != nullptr.  N = (rope_hq + 2 rope_hkv) * 128; q heads go to C, k/v heads to the pools.
+  const __nv_bfloat16* rope_table = nullptr;  // [M, 128]: cos[0..64) | sin[0..64) per token (rope_table())
+  __nv_bfloat16* k_pool = nullptr;         // paged pools [pages, 128, Hkv, 128] (nullptr: k/v stay in C)
+  __nv_bfloat16* v_pool = nullptr;
+  const int32_t* page_table = nullptr;
+  int cache_pos0 = 0;
+  int rope_hq = 0, rope_hkv = 0;
 };
 
 int set_workspace(void* ptr, size_t bytes);
@@ -30,6 +39,8 @@ int gemm_skinny_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, in
                      int ldc, int M, int N, int K, const GemmEpilogue& epi, int pair, cudaStream_t stream);  // -1: not handled
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
               int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream);
+int gemm_qkv_rope_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, __nv_bfloat16* C,
+                       int ldc, int M, int N, int K, const GemmEpilogue& epi, cudaStream_t stream);  // -1: not covered
 int gemm_bf16_cfg(int block_n, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw,
                   __nv_bfloat16* C, int ldc, int M, int N, int K, const GemmEpilogue& epi,
                   cudaStream_t stream);
@@ -88,6 +99,8 @@ int embed_splice(const __nv_bfloat16* table, const __nv_bfloat16* media, const i
                  __nv_bfloat16* out, int rows, int cols, cudaStream_t stream);
 // In-place rotate-half RoPE on q and k heads of a fused qkv buffer [S, (Hq+2Hkv)*D], then scatter
 // k and v rows into the paged KV pool.
+int rope_table(const int32_t* positions, int S, int D, const float* inv_freq, __nv_bfloat16* table,
+               cudaStream_t stream);
 int rope_kv_append(__nv_bfloat16* qkv, const int32_t* positions, int S, int Hq, int Hkv, int D,
                    const float* inv_freq, __nv_bfloat16* k_pool, __nv_bfloat16* v_pool,
                    const int32_t* page_table, int cache_pos0, cudaStream_t stream);

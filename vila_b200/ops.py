@@ -227,6 +227,44 @@ def rope_kv_append(qkv: torch.Tensor, positions: torch.Tensor, Hq: int, Hkv: int
                                           _stream()), "vila_rope_kv_append")
 
 
+def rope_table(positions: torch.Tensor, D: int, inv_freq: torch.Tensor) -> torch.Tensor:
+    """cos | sin table [S, D] bf16 of a request's positions (shared by all layers and heads)."""
+    assert positions.dtype == torch.int32 and inv_freq.dtype == torch.float32 and positions.is_cuda
+    S = positions.numel()
+    table = torch.empty((S, D), dtype=torch.bfloat16, device=positions.device)
+    check(_lib.load().vila_rope_table(_p(positions), S, D, _p(inv_freq), _p(table), _stream()),
+          "vila_rope_table")
+    return table
+
+
+def linear_qkv_rope(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
+                    table: torch.Tensor, Hq: int, Hkv: int, D: int,
+                    k_pool: Optional[torch.Tensor] = None, v_pool: Optional[torch.Tensor] = None,
+                    page_table: Optional[torch.Tensor] = None, cache_pos0: int = 0,
+                    static_w: bool = False) -> Optional[torch.Tensor]:
+    """q/k/v projection + RoPE + KV-cache append in one kernel (short prefill chunks: M <= 384,
+    head_dim 128; table = rope_table(positions)).  Returns qkv [M, (Hq+2Hkv)*D] whose q heads are
+    rotated (k / v heads live in the pools when given), or None when the shape is not covered
+    (caller: linear + rope_kv_append)."""
+    _chk(x, "x"); _chk(w, "w")
+    M, K = x.shape
+    N = (Hq + 2 * Hkv) * D
+    if D != 128 or M > 384 or M == 0:
+        return None
+    assert w.shape == (N, K) and x.stride(1) == 1 and w.stride(1) == 1
+    assert table.shape == (M, D) and table.dtype == torch.bfloat16 and table.is_contiguous()
+    ensure_workspace(x.device)
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    rc = _lib.load().vila_linear_qkv_rope(_p(x), x.stride(0), _p(w), w.stride(0), _p(bias), _p(out),
+                                          out.stride(0), M, K, Hq, Hkv, D, _p(table),
+                                          _p(k_pool), _p(v_pool), _p(page_table), cache_pos0,
+                                          2 if static_w else 0, _stream())
+    if rc == 3:
+        return None
+    check(rc, "vila_linear_qkv_rope")
+    return out
+
+
 def gemv(x: torch.Tensor, w: torch.Tensor, *, bias=None, norm_w=None, norm_eps: float = 1e-6,
          residual=None, swiglu: bool = False, out: Optional[torch.Tensor] = None,
          argmax_key: Optional[torch.Tensor] = None, write_out: bool = True,
