@@ -35,6 +35,17 @@ for st in $STAGES; do
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tcgen05 -s 30 -c 3 \
           -f -o gpurun_out/prof_gemm python bench.py --profile --steps 1 > gpurun_out/ncu_gemm.log 2>&1
       echo "== ncu gemm rc=$?" ;;
+    ncu_skinny)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_skinny -s 2 -c 1 \
+          -f -o gpurun_out/prof_skinny python tools/profile_skinny.py > gpurun_out/ncu_skinny.log 2>&1
+      echo "== ncu skinny rc=$?" ;;
+    ncu_gemm_big)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tcgen05 -s 2 -c 1 \
+          -f -o gpurun_out/prof_gemm_big python tools/profile_gemm_big.py > gpurun_out/ncu_gemm_big.log 2>&1
+      echo "== ncu gemm big rc=$?" ;;
+    gemm_table)
+      timeout 600 python tools/bench_gemm.py > gpurun_out/bench_gemm.log 2>&1
+      echo "== gemm table rc=$?"; tail -n 3 gpurun_out/bench_gemm.log | cut -c1-300 ;;
     ncu_fmha)
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:fmha_fwd -s 10 -c 2 \
           -f -o gpurun_out/prof_fmha python bench.py --profile --steps 1 > gpurun_out/ncu_fmha.log 2>&1
