@@ -378,6 +378,9 @@ def run_sp(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if "RANK" not in os.environ:  # plain `python bench.py --workload sp_prefill`: a 1-rank group
+        os.environ.update({"RANK": "0", "WORLD_SIZE": "1", "MASTER_ADDR": "127.0.0.1",
+                           "MASTER_PORT": os.environ.get("MASTER_PORT", "29533")})
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from vila_b200 import sp
     from vila_b200.model import LlavaLlamaModel, nvila_video_8b

@@ -43,6 +43,7 @@ def _tiles128(M, N):
 GEMM_SHAPES = [
     (128, 128, 64), (256, 256, 128), (1024, 1152, 1152), (280, 3584, 3584), (1000, 4304, 1152),
     (1024, 1152, 4304), (2048, 1152, 592), (24, 512, 1536), (257, 3584, 4608), (130, 136, 72),
+    (256, 512, 1088),  # odd number of k-blocks (17): uneven halves for the split-K pairs
 ]
 
 
