@@ -7,6 +7,8 @@ output produced by the reference implementation:
   projector_*.pt     reference MultimodalProjector for the three NVILA projector types
   arch_glue.pt       reference llava_arch.py excerpts (dynamic-S2 encode_images, _embed splice), run
                      unmodified via ast extraction
+  media_preprocess.pt  reference mm_utils.dynamic_s2_preprocess on seeded images: block sizes + per-tile
+                     pixel sums and a 16x16 thumbnail of every tile
   qwen2_tiny.pt      transformers Qwen2ForCausalLM logits + greedy ids (the reference's LLM is this
                      third-party class; pinned transformers==4.46.0, here the installed version)
 """
@@ -168,10 +170,37 @@ def gen_qwen2():
                OUT / "qwen2_tiny.pt")
 
 
+MEDIA_SIZES = [(448, 448), (1600, 800), (800, 1600), (333, 1000), (1920, 1080), (640, 480), (97, 131), (3000, 500)]
+
+
+def media_test_image(w: int, h: int, seed: int):
+    """Seeded synthetic RGB image (numpy RandomState: identical in the test)."""
+    import numpy as np
+    from PIL import Image
+    return Image.fromarray(np.random.RandomState(seed).randint(0, 256, (h, w, 3), dtype=np.uint8))
+
+
+def gen_media():
+    import numpy as np
+    srcs = V.extract_functions(REF / "llava/mm_utils.py", ["find_closest_aspect_ratio", "dynamic_s2_preprocess"])
+    ns = {}
+    exec(srcs["find_closest_aspect_ratio"], ns)
+    exec(srcs["dynamic_s2_preprocess"], ns)
+    out = []
+    for i, (w, h) in enumerate(MEDIA_SIZES):
+        tiles, bs = ns["dynamic_s2_preprocess"](media_test_image(w, h, 100 + i), s2_scales=[448, 896, 1344],
+                                                max_num=12, image_size=448)
+        arrs = [np.asarray(t, dtype=np.int64) for t in tiles]
+        out.append({"size": (w, h), "seed": 100 + i, "block_size": tuple(bs), "n_tiles": len(tiles),
+                    "tile_sums": torch.tensor([int(a.sum()) for a in arrs]),
+                    "tile_thumbs": torch.tensor(np.stack([a[::28, ::28, :] for a in arrs]), dtype=torch.uint8)})
+    torch.save(out, OUT / "media_preprocess.pt")
+
+
 if __name__ == "__main__":
     assert REF.exists(), "needs /root/reference"
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(4)
-    gen_siglip(); gen_projector(); gen_arch_glue(); gen_qwen2()
+    gen_siglip(); gen_projector(); gen_arch_glue(); gen_qwen2(); gen_media()
     for f in sorted(OUT.glob("*.pt")):
         print(f.name, f.stat().st_size)

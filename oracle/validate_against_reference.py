@@ -210,6 +210,65 @@ def check_arch_glue():
     report("TSP pool (4,2,2)", (r - m).abs().max().item(), 0)
 
 
+def check_media_preprocess():
+    """mm_utils.dynamic_s2_preprocess / find_closest_aspect_ratio (reference, executed from source) vs
+    the host-side tiling of vila_b200.model.media (product code, host logic only) on a sweep of image
+    sizes: identical block sizes and bit-identical tile pixels."""
+    import numpy as np
+    from PIL import Image
+    from vila_b200.model import media
+    srcs = extract_functions(REF / "llava/mm_utils.py", ["find_closest_aspect_ratio", "dynamic_s2_preprocess"])
+    ns = {}
+    exec(srcs["find_closest_aspect_ratio"], ns)
+    exec(srcs["dynamic_s2_preprocess"], ns)
+    rng = np.random.RandomState(7)
+    worst, n_bad = 0.0, 0
+    sizes = [(448, 448), (1600, 800), (800, 1600), (333, 1000), (1920, 1080), (640, 480), (97, 131), (3000, 500)]
+    for (w, h) in sizes:
+        img = Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8))
+        ref_tiles, ref_bs = ns["dynamic_s2_preprocess"](img, s2_scales=[448, 896, 1344], max_num=12, image_size=448)
+        my_tiles, my_bs = media.dynamic_s2_preprocess(img, [448, 896, 1344], 12, 448)
+        if tuple(ref_bs) != tuple(my_bs) or len(ref_tiles) != len(my_tiles):
+            n_bad += 1
+            continue
+        for a, b in zip(ref_tiles, my_tiles):
+            worst = max(worst, float(np.abs(np.asarray(a, dtype=np.int32) - np.asarray(b, dtype=np.int32)).max()))
+    report(f"dynamic_s2_preprocess block sizes ({len(sizes)} image sizes)", float(n_bad), 0)
+    report("dynamic_s2_preprocess tile pixels", worst, 0)
+
+
+def check_encoders():
+    """BasicImageEncoder._process_features / TSPVideoEncoder._process_features (reference source) vs the
+    oracle's image_encoder / tsp_video_encoder."""
+    img_src = extract_functions(REF / "llava/model/encoders/image/basic.py", ["_process_features"])["_process_features"]
+    tsp_srcs = extract_functions(REF / "llava/model/encoders/video/tsp.py", ["pool", "_process_features"])
+    ns = {"torch": torch, "Optional": object}
+    exec(tsp_srcs["pool"], ns)
+    vid_src = extract_functions(REF / "llava/model/encoders/video/basic.py", ["_process_features"])["_process_features"]
+    body = "class Base:\n" + textwrap.indent(img_src, "    ") + "\n"
+    body += "class VideoBase:\n" + textwrap.indent(vid_src, "    ") + "\n"
+    body += "class TSP(VideoBase):\n" + textwrap.indent(tsp_srcs["_process_features"], "    ") + "\n"
+    exec(compile(body, "<reference encoder excerpts>", "exec"), ns)
+    torch.manual_seed(11)
+    H = 8
+    start, end, sep = torch.randn(2, H), torch.randn(1, H), torch.randn(1, H)
+    feats = torch.randn(3, 16, H)
+    base = ns["Base"]()
+    ref = [base._process_features(f, start, end) for f in feats]
+    mine = O.image_encoder(list(feats), end, start)
+    report("BasicImageEncoder._process_features", max((a - b).abs().max().item() for a, b in zip(ref, mine)), 0)
+    vbase = ns["VideoBase"]()
+    vfeat = torch.randn(5, 16, H)
+    report("BasicVideoEncoder._process_features",
+           (vbase._process_features(vfeat, start, end) - O.video_encoder(vfeat, end, start)).abs().max().item(), 0)
+    tsp = ns["TSP"]()
+    tsp.pool_sizes = [(4, 1, 1), (2, 2, 2)]
+    vid = torch.randn(8, 16, H)
+    ref_v = tsp._process_features(vid, start, end, sep)
+    mine_v = O.tsp_video_encoder(vid, tsp.pool_sizes, end, start, sep)
+    report("TSPVideoEncoder._process_features", (ref_v - mine_v).abs().max().item(), 0)
+
+
 def check_qwen2():
     from transformers import Qwen2Config, Qwen2ForCausalLM
     torch.manual_seed(3)
@@ -254,6 +313,8 @@ if __name__ == "__main__":
     check_siglip()
     check_projector()
     check_arch_glue()
+    check_media_preprocess()
+    check_encoders()
     check_qwen2()
     print("FAILED:" if FAILED else "ALL OK", FAILED)
     sys.exit(1 if FAILED else 0)

@@ -94,3 +94,24 @@ def test_dynamic_s2_preprocess_block_sizes():
     assert abs(float(tensors[0][0].mean()) - (120 / 255 - 0.5) / 0.5) < 1e-2
     text, images = media.extract_media(["look: ", img, "what?"], cfg)
     assert text == "look: <image>\nwhat?" and len(images) == 1
+
+
+def test_dynamic_s2_preprocess_matches_reference_fixture():
+    """Host-side tiling (vila_b200.model.media) against tests/golden/media_preprocess.pt, which holds the
+    output of the REFERENCE's mm_utils.dynamic_s2_preprocess (llava/mm_utils.py:341-405) on the same
+    seeded images (oracle/gen_golden.py): block sizes, tile count, exact pixel sums and a strided
+    thumbnail of every tile."""
+    import numpy as np
+    from PIL import Image
+    from vila_b200.model import media
+    fx = torch.load(ROOT / "tests" / "golden" / "media_preprocess.pt")
+    assert len(fx) == 8
+    for item in fx:
+        w, h = item["size"]
+        img = Image.fromarray(np.random.RandomState(item["seed"]).randint(0, 256, (h, w, 3), dtype=np.uint8))
+        tiles, bs = media.dynamic_s2_preprocess(img, [448, 896, 1344], 12, 448)
+        assert tuple(bs) == tuple(item["block_size"]) and len(tiles) == item["n_tiles"], item["size"]
+        arrs = [np.asarray(t, dtype=np.int64) for t in tiles]
+        assert [int(a.sum()) for a in arrs] == item["tile_sums"].tolist(), item["size"]
+        thumbs = np.stack([a[::28, ::28, :] for a in arrs]).astype(np.uint8)
+        assert np.array_equal(thumbs, item["tile_thumbs"].numpy()), item["size"]
