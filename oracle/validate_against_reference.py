@@ -237,6 +237,30 @@ def check_media_preprocess():
     report("dynamic_s2_preprocess tile pixels", worst, 0)
 
 
+def check_pixel_preprocess():
+    """processor.preprocess(...) as called by mm_utils.process_image (:476,505) — the reference pins
+    transformers==4.46.0 whose SiglipImageProcessor resizes through PIL (bicubic) exactly like
+    vila_b200.model.media._to_tensor; the installed 5.x processor interpolates in torch, so agreement is
+    exact for 448x448 inputs and within one 8-bit level (2/255 after normalisation) otherwise."""
+    import numpy as np
+    from PIL import Image
+    from transformers import SiglipImageProcessor
+    from vila_b200.model import media
+    proc = SiglipImageProcessor(size={"height": 448, "width": 448})
+    rng = np.random.RandomState(3)
+    worst_same, worst_resized = 0.0, 0.0
+    for (w, h) in [(448, 448), (640, 480), (97, 131), (1600, 800)]:
+        img = Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8))
+        ref = proc.preprocess(img, return_tensors="pt")["pixel_values"][0]
+        d = float((ref - media._to_tensor(img, 448)).abs().max())
+        if (w, h) == (448, 448):
+            worst_same = max(worst_same, d)
+        else:
+            worst_resized = max(worst_resized, d)
+    report("pixel preprocess 448x448 vs SiglipImageProcessor", worst_same, 1e-6)
+    report("pixel preprocess resized vs SiglipImageProcessor (1 level)", worst_resized, 2 / 255 + 1e-6)
+
+
 def check_encoders():
     """BasicImageEncoder._process_features / TSPVideoEncoder._process_features (reference source) vs the
     oracle's image_encoder / tsp_video_encoder."""
@@ -314,6 +338,7 @@ if __name__ == "__main__":
     check_projector()
     check_arch_glue()
     check_media_preprocess()
+    check_pixel_preprocess()
     check_encoders()
     check_qwen2()
     print("FAILED:" if FAILED else "ALL OK", FAILED)
