@@ -334,7 +334,7 @@ def embed_splice(input_ids: torch.Tensor, embed_table: torch.Tensor,
             if ids_k[pos] in tok2name:
                 end = pos + 1
                 inp = queues[tok2name[ids_k[pos]]].popleft()
-                lab = torch.full([inp.shape[0]], IGNORE_INDEX, dtype=labs[k].dtype)
+                lab = torch.full([inp.shape[0]], IGNORE_INDEX, dtype=labs[k].dtype, device=labs[k].device)
             else:
                 end = pos
                 while end < len(labs[k]) and ids_k[end] not in tok2name:
@@ -352,12 +352,12 @@ def embed_splice(input_ids: torch.Tensor, embed_table: torch.Tensor,
     # __batchify_sequence
     hidden = inputs_m[0].shape[1]
     max_len = max(x.shape[0] for x in inputs_m)
-    mask = torch.ones((bsz, max_len), dtype=torch.bool)
+    mask = torch.ones((bsz, max_len), dtype=torch.bool, device=inputs_m[0].device)
     ins_p, lab_p = [], []
     for k in range(bsz):
         n = inputs_m[k].shape[0]
-        pad_i = torch.zeros((max_len - n, hidden), dtype=inputs_m[k].dtype)
-        pad_l = torch.full((max_len - n,), IGNORE_INDEX, dtype=labels_m[k].dtype)
+        pad_i = torch.zeros((max_len - n, hidden), dtype=inputs_m[k].dtype, device=inputs_m[k].device)
+        pad_l = torch.full((max_len - n,), IGNORE_INDEX, dtype=labels_m[k].dtype, device=labels_m[k].device)
         if padding_side == "right":
             mask[k, n:] = False
             ins_p.append(torch.cat([inputs_m[k], pad_i], 0))
@@ -389,7 +389,7 @@ def rope_inv_freq(head_dim: int, theta: float) -> torch.Tensor:
 
 def rope_cos_sin(position_ids: torch.Tensor, head_dim: int, theta: float, dtype):
     """cos/sin caches (modeling_qwen2.py:113-134): fp32 outer product, cat, cos/sin, cast."""
-    inv = rope_inv_freq(head_dim, theta)
+    inv = rope_inv_freq(head_dim, theta).to(position_ids.device)
     freqs = position_ids.to(torch.float32)[:, None] * inv[None, :]
     emb = torch.cat([freqs, freqs], dim=-1)
     return emb.cos().to(dtype), emb.sin().to(dtype)
@@ -424,12 +424,18 @@ def qwen2_attention(x, p, prefix: str, cfg: Qwen2Cfg, position_ids, past_kv=None
     kk = k.repeat_interleave(rep, dim=0)
     vv = v.repeat_interleave(rep, dim=0)
     Sk = kk.shape[1]
-    att = torch.matmul(q, kk.transpose(1, 2)) / math.sqrt(D)  # :273
-    mask = torch.full((S, Sk), float("-inf"), dtype=att.dtype)
+    mask = torch.full((S, Sk), float("-inf"), dtype=torch.float32, device=x.device)
     mask = torch.triu(mask, diagonal=Sk - S + 1)
-    att = att + mask
-    att = F.softmax(att, dim=-1, dtype=torch.float32).to(q.dtype)  # :290
-    o = torch.matmul(att, vv).transpose(0, 1).reshape(S, H * D)
+    # Same arithmetic per head; heads are processed in groups only to bound the [h, S, Sk] score
+    # tensor for long sequences (64-frame video: S = 16.5K -> 1 GB per head in fp32).
+    hstep = max(1, min(H, (1 << 28) // max(1, S * Sk)))
+    outs = []
+    for h0 in range(0, H, hstep):
+        att = torch.matmul(q[h0:h0 + hstep], kk[h0:h0 + hstep].transpose(1, 2)) / math.sqrt(D)  # :273
+        att = att + mask.to(att.dtype)
+        att = F.softmax(att, dim=-1, dtype=torch.float32).to(q.dtype)  # :290
+        outs.append(torch.matmul(att, vv[h0:h0 + hstep]))
+    o = torch.cat(outs, dim=0).transpose(0, 1).reshape(S, H * D)
     return F.linear(o, p[prefix + "o_proj.weight"]), new_kv
 
 
@@ -440,13 +446,13 @@ def qwen2_mlp(x, p, prefix: str):
 
 
 def qwen2_forward(inputs_embeds, p, cfg: Qwen2Cfg, position_ids=None, past=None,
-                  last_only: bool = False):
+                  last_only: bool = False, return_hidden: bool = False):
     """Qwen2ForCausalLM.forward for one sequence (decoder layer: modeling_qwen2.py:633-706).
     inputs_embeds [S, hidden] -> (logits [S or 1, V], new_past)."""
     S = inputs_embeds.shape[0]
     past_len = 0 if past is None else past[0][0].shape[1]
     if position_ids is None:
-        position_ids = torch.arange(past_len, past_len + S)
+        position_ids = torch.arange(past_len, past_len + S, device=inputs_embeds.device)
     x = inputs_embeds
     new_past = []
     for i in range(cfg.num_hidden_layers):
@@ -458,9 +464,12 @@ def qwen2_forward(inputs_embeds, p, cfg: Qwen2Cfg, position_ids=None, past=None,
         x = x + a
         h = rms_norm(x, p[pre + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
         x = x + qwen2_mlp(h, p, pre + "mlp.")
+    hidden = x  # last decoder layer's output (input of the final norm)
     x = rms_norm(x, p["model.norm.weight"], cfg.rms_norm_eps)
     if last_only:
         x = x[-1:]
+    if return_hidden:
+        return F.linear(x, p["lm_head.weight"]), new_past, hidden
     return F.linear(x, p["lm_head.weight"]), new_past
 
 
@@ -513,13 +522,13 @@ class VilaOracleModel:
 
     def embed(self, input_ids, images: List[torch.Tensor], block_sizes=None):
         """_embed for media = {"image": images} (llava_arch.py:412-490)."""
-        end = F.embedding(torch.tensor(self.newline_token_ids), self.llm["model.embed_tokens.weight"])
+        table = self.llm["model.embed_tokens.weight"]
+        end = F.embedding(torch.tensor(self.newline_token_ids, device=table.device), table)
         media = {}
         if images:
             feats = self.encode_images(torch.stack(images, 0), block_sizes)
             media["image"] = image_encoder(list(feats), end)
-        return embed_splice(input_ids, self.llm["model.embed_tokens.weight"], media,
-                            {"image": self.image_token_id})
+        return embed_splice(input_ids.to(table.device), table, media, {"image": self.image_token_id})
 
     def forward_logits(self, input_ids, images, block_sizes=None):
         emb, _, _ = self.embed(input_ids, images, block_sizes)

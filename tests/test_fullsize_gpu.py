@@ -1,24 +1,52 @@
-"""GPU: BASELINE.json's full-size configurations through size-independent properties (the CPU oracle
-cannot finish these sizes in seconds):
-  #2 NVILA-8B request        greedy decode is bit-reproducible; KV-cached decode == re-prefill
-  #3 NVILA-Video-8B 64 frames batched vision encode == per-frame encode (bf16 noise; each bit-reproducible);
-                             chunked prefill (S = 16.4K in two chunks) == single prefill
-  #4 dynamic-S2 35 tiles     encode_images shape / finiteness / reproducibility, single-tile path
-One 8B-scale random-init model is shared by the module (~20 s to build on a B200)."""
+"""GPU: BASELINE.json's configurations at their NAMED sizes (full width, full depth).
+
+(a) against the oracle: `oracle/vila_oracle.py` is plain PyTorch, so at these sizes it is evaluated on
+    the device (torch's own fp32 library kernels, TF32 off = the truth; the same code in bf16 = the
+    reference's own GPU numerics: cuBLAS bf16 GEMMs, fp32 softmax, unfused rounding points) on the
+    model's state dict.  The CPU evaluation of the same oracle is what the tiny-config tests in
+    test_model_gpu.py and the golden fixtures pin.  Tolerance: tests/helpers.check_close.
+      #1 NVILA-Lite-3B   1 tile, mlp_downsample_3x3_fix, 36-layer Qwen2.5-3B-shaped LLM: logits + greedy ids
+      #2 NVILA-8B        1 x 448^2, S = 279: tower (26 layers), projector, all-row logits, 24 greedy ids
+      #3 NVILA-Video-8B  64 frames: batched tower + 2x2_fix projector; 28-layer prefill at S = 16,470
+      #4 dynamic-S2      35 tiles, block (5,6): tower + S2 merge + C=3456 projector + re-stitch
+(b) size-independent properties: greedy decode bit-reproducible; KV-cached decode == re-prefill;
+    batched encode == per-frame encode; chunked prefill == single prefill.
+One 8B-scale random-init model is alive at a time (~20 s to build on a B200)."""
 import pytest
 import torch
 
+from tests.helpers import check_close, greedy_ids_match, oracle_from_state_dict
+
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_truth():
+    """the fp32 oracle must really be fp32 on the device"""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    yield
+    torch.cuda.empty_cache()
+
+
+def device_oracles(model):
+    sd = model.state_dict()
+    o32 = oracle_from_state_dict(sd, model.config, torch.float32, device="cuda")
+    o16 = oracle_from_state_dict(sd, model.config, torch.bfloat16, device="cuda")
+    return o32, o16
 
 _MODELS = {}
 
 
 def get_model(kind):
-    from vila_b200.model import LlavaLlamaModel, nvila_8b, nvila_8b_dynamic_s2, nvila_video_8b
+    from vila_b200.model import (LlavaLlamaModel, nvila_8b, nvila_8b_dynamic_s2, nvila_lite_3b,
+                                 nvila_video_8b)
     if kind not in _MODELS:
         _MODELS.clear()  # one 15 GB model at a time
         torch.cuda.empty_cache()
-        cfg = {"image": nvila_8b, "video": nvila_video_8b, "s2": nvila_8b_dynamic_s2}[kind]()
+        cfg = {"image": nvila_8b, "video": nvila_video_8b, "s2": nvila_8b_dynamic_s2,
+               "lite": nvila_lite_3b}[kind]()
         _MODELS[kind] = LlavaLlamaModel(cfg, device="cuda").init_random(0, device_rng=True)
     return _MODELS[kind]
 
@@ -52,6 +80,46 @@ def test_cfg2_request_reproducible_and_cache_consistent(cuda):
         assert int(torch.argmax(lg)) == int(a[0, 8])
 
 
+def test_cfg2_matches_oracle_full_depth(cuda):
+    """BASELINE configs[1] at its named size against the oracle, stage by stage."""
+    model = get_model("image")
+    cfg = model.config
+    g = torch.Generator().manual_seed(3)
+    px = torch.randn(3, 448, 448, generator=g).to(torch.bfloat16)
+    ids = torch.randint(0, 151643, (22,), generator=g).tolist()
+    ids.insert(9, cfg.image_token_id)
+    ids = torch.tensor([ids])
+    o32, o16 = device_oracles(model)
+    pxd = px.cuda()
+    feats = model.vision_tower(pxd[None]).clone()
+    t32 = o32.tower(pxd[None].float())
+    check_close("cfg2 tower (26 layers, 1x448^2)", feats, t32, o16.tower(pxd[None]))
+    enc = model.encode_images(pxd[None]).clone()
+    check_close("cfg2 tower+projector", enc, o32.project(t32), o16.encode_images(pxd[None]))
+    out = model(input_ids=ids, media={"image": [pxd]})
+    truth = o32.forward_logits(ids, [pxd.float()])
+    assert out.logits.shape[1:] == truth.shape == (279, cfg.llm_cfg.vocab_size)
+    check_close("cfg2 logits [279 x 152064] (28 layers)", out.logits[0], truth,
+                o16.forward_logits(ids, [pxd]))
+    new = model.generate(input_ids=ids, media={"image": [pxd]}, max_new_tokens=24, eos_token_id=None)
+    want, logits = o32.generate(ids, [pxd.float()], 24)
+    greedy_ids_match(new[0].tolist(), want, logits, 3 * 2 ** -8 * logits.abs().max().item())
+
+
+def test_generate_content_public_api(cuda):
+    from PIL import Image
+    model = get_model("image")
+    img = Image.new("RGB", (640, 480), (200, 40, 90))
+    from types import SimpleNamespace
+    gc = SimpleNamespace(max_new_tokens=8, do_sample=False, eos_token_id=list(model.config.eos_token_ids),
+                         pad_token_id=model.config.pad_token_id, max_length=None)
+    text = model.generate_content([img, "Describe the image."], generation_config=gc)
+    assert isinstance(text, str) and len(text.split()) <= 8
+    # the default generation config mirrors llava_arch.py:950-963
+    d = model.default_generation_config
+    assert d.eos_token_id == model.tokenizer.stop_token_ids and d.max_length == model.tokenizer.model_max_length
+
+
 def test_cfg3_video_batch_invariance_and_chunked_prefill(cuda):
     model = get_model("video")
     cfg = model.config
@@ -83,6 +151,42 @@ def test_cfg3_video_batch_invariance_and_chunked_prefill(cuda):
     assert torch.equal(cache.pool[5, 0, :125], cache2.pool[5, 0, :125])
 
 
+def test_cfg3_matches_oracle_full_depth(cuda):
+    """BASELINE configs[2]: 64 frames through the batched tower (256x256 CTA-pair GEMM tiles, two-tile
+    FMHA), the 2x2_fix projector, the video encoder and the 28-layer prefill at S = 16,470 (pair
+    tiles + fmha2 causal GQA over the paged cache), against the oracle on the device."""
+    model = get_model("video")
+    cfg = model.config
+    g = torch.Generator(device="cuda").manual_seed(4)
+    frames = torch.randn(64, 3, 448, 448, device="cuda", generator=g).to(torch.bfloat16)
+    o32, o16 = device_oracles(model)
+    feats = model.vision_tower(frames).clone()
+    t32 = o32.tower(frames.float())
+    t16 = o16.tower(frames)
+    check_close("cfg3 tower (26 layers, 64 frames)", feats, t32, t16)
+    enc = model.encode_images(frames).clone()
+    p32 = o32.project(t32)
+    check_close("cfg3 tower+projector (2x2_fix)", enc, p32, o16.project(t16))
+    del t32, t16, feats
+    from oracle import vila_oracle as O
+    table = model.llm.model.embed_tokens.weight
+    end32 = table[list(cfg.newline_token_ids)].float()
+    vid32 = O.video_encoder(p32, end32)
+    got_vid = model.encoders["video"]([frames], {})[0]
+    assert got_vid.shape == vid32.shape == (64 * 257, cfg.hidden_size)
+    text = table[torch.arange(100, 122, device="cuda")]
+    # the SAME bf16 sequence goes into both LLMs (isolates the LLM; the vision error is checked above)
+    seq = torch.cat([text[:10], got_vid, text[10:]], 0)
+    llm = model.llm
+    cache = llm.new_cache(seq.shape[0])
+    hid = llm.prefill_hidden(seq, cache)
+    lg = llm.logits_from_hidden(hid[-1:])
+    l32, _, h32 = O.qwen2_forward(seq.float(), o32.llm, o32.lcfg, last_only=True, return_hidden=True)
+    l16, _, h16 = O.qwen2_forward(seq, o16.llm, o16.lcfg, last_only=True, return_hidden=True)
+    check_close("cfg3 prefill hidden [16470 x 3584] (28 layers)", hid, h32, h16)
+    check_close("cfg3 last-token logits", lg, l32, l16)
+
+
 def test_cfg4_dynamic_s2_full_size(cuda):
     model = get_model("s2")
     cfg = model.config
@@ -101,15 +205,52 @@ def test_cfg4_dynamic_s2_full_size(cuda):
     assert single.shape == (1, 256, cfg.hidden_size) and torch.isfinite(single.float()).all()
 
 
-def test_generate_content_public_api(cuda):
-    from PIL import Image
-    model = get_model("image")
-    img = Image.new("RGB", (640, 480), (200, 40, 90))
-    from types import SimpleNamespace
-    gc = SimpleNamespace(max_new_tokens=8, do_sample=False, eos_token_id=list(model.config.eos_token_ids),
-                         pad_token_id=model.config.pad_token_id, max_length=None)
-    text = model.generate_content([img, "Describe the image."], generation_config=gc)
-    assert isinstance(text, str) and len(text.split()) <= 8
-    # the default generation config mirrors llava_arch.py:950-963
-    d = model.default_generation_config
-    assert d.eos_token_id == model.tokenizer.stop_token_ids and d.max_length == model.tokenizer.model_max_length
+
+def test_cfg4_matches_oracle_full_depth(cuda):
+    """BASELINE configs[3] (producible layout): 1 + 4 + 5x6 = 35 tiles -> tower -> S2
+    merge to the largest scale -> C = 3456 projector -> re-stitch, against the oracle; plus the
+    fp32 / fp16 pixel inputs the reference feeds."""
+    model = get_model("s2")
+    cfg = model.config
+    bs = (5, 6)
+    n_tiles = 1 + 4 + bs[0] * bs[1]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    tiles = torch.randn(n_tiles, 3, 448, 448, device="cuda", generator=g).to(torch.bfloat16)
+    o32, o16 = device_oracles(model)
+    got = model.encode_images(tiles, block_sizes=[bs])
+    t32 = o32.encode_images(tiles.float(), [bs])
+    t16 = o16.encode_images(tiles, [bs])
+    assert len(t32) == 1 and got[0].shape == t32[0].shape
+    check_close("cfg4 dynamic-S2 encode_images (35 tiles, C=3456)", got[0], t32[0], t16[0])
+    # single tile (block_size None) through the share-tile path
+    one = model.encode_images(tiles[:1], block_sizes=[None])
+    check_close("cfg4 dynamic-S2 single tile", one[0], o32.encode_images(tiles[:1].float(), [None])[0],
+                o16.encode_images(tiles[:1], [None])[0])
+    # fp32 / fp16 pixels (media._to_tensor gives fp32; the reference calls .half())
+    for dt in (torch.float32, torch.float16):
+        again = model.encode_images(tiles[:1].to(dt), block_sizes=[None])
+        assert torch.equal(again[0], one[0])
+
+
+def test_cfg1_lite3b_matches_oracle_full_depth(cuda):
+    """BASELINE configs[0]'s architecture (NVILA-Lite-3B: 3x3_fix projector -> 121 tokens, 36-layer
+    Qwen2.5-3B-shaped LLM with 16/2 heads) on the GPU path: logits and 32 greedy ids vs the oracle."""
+    model = get_model("lite")
+    cfg = model.config
+    g = torch.Generator().manual_seed(6)
+    px = torch.randn(3, 448, 448, generator=g).to(torch.bfloat16).cuda()
+    ids = torch.randint(0, 151643, (22,), generator=g).tolist()
+    ids.insert(5, cfg.image_token_id)
+    ids = torch.tensor([ids])
+    o32, o16 = device_oracles(model)
+    enc = model.encode_images(px[None]).clone()
+    assert enc.shape == (1, 121, cfg.hidden_size)
+    check_close("cfg1 tower+projector (3x3_fix)", enc, o32.encode_images(px[None].float()),
+                o16.encode_images(px[None]))
+    out = model(input_ids=ids, media={"image": [px]})
+    truth = o32.forward_logits(ids, [px.float()])
+    assert out.logits.shape[1] == truth.shape[0] == 22 + 122
+    check_close("cfg1 logits (36 layers)", out.logits[0], truth, o16.forward_logits(ids, [px]))
+    new = model.generate(input_ids=ids, media={"image": [px]}, max_new_tokens=32, eos_token_id=None)
+    want, logits = o32.generate(ids, [px.float()], 32)
+    greedy_ids_match(new[0].tolist(), want, logits, 3 * 2 ** -8 * logits.abs().max().item())

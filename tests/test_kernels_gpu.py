@@ -239,19 +239,28 @@ def test_rmsnorm(cuda, rows, cols):
 # attention
 # ------------------------------------------------------------------------------------------------
 def ref_attention(q, k, v, causal, scale):
-    """q [B,Sq,Hq,D], k/v [B,Sk,Hkv,D] fp32 -> [B,Sq,Hq,D]; softmax fp32, P cast to bf16 (reference)."""
+    """q [B,Sq,Hq,D], k/v [B,Sk,Hkv,D] fp32 -> [B,Sq,Hq,D]; softmax fp32, P cast to bf16 (reference).
+    Heads are processed in groups only to bound the score tensor at long sequence lengths."""
     B, Sq, Hq, D = q.shape
     Sk, Hkv = k.shape[1], k.shape[2]
     rep = Hq // Hkv
-    qq = q.permute(0, 2, 1, 3).float()
-    kk = k.permute(0, 2, 1, 3).float().repeat_interleave(rep, dim=1)
-    vv = v.permute(0, 2, 1, 3).float().repeat_interleave(rep, dim=1)
-    att = qq @ kk.transpose(-1, -2) * scale
+    mask = None
     if causal:
         mask = torch.ones(Sq, Sk, dtype=torch.bool, device=q.device).tril(Sk - Sq)
-        att = att.masked_fill(~mask, float("-inf"))
-    p = rb(torch.softmax(att, dim=-1))
-    return (p @ vv).permute(0, 2, 1, 3)
+    step = max(1, min(Hq, (1 << 29) // max(1, B * Sq * Sk)))
+    out = torch.empty(B, Sq, Hq, D, dtype=torch.float32, device=q.device)
+    for h0 in range(0, Hq, step):
+        hs = list(range(h0, min(Hq, h0 + step)))
+        qq = q[:, :, hs].permute(0, 2, 1, 3).float()
+        kk = k[:, :, [h // rep for h in hs]].permute(0, 2, 1, 3).float()
+        vv = v[:, :, [h // rep for h in hs]].permute(0, 2, 1, 3).float()
+        att = qq @ kk.transpose(-1, -2) * scale
+        if mask is not None:
+            att = att.masked_fill(~mask, float("-inf"))
+        p = rb(torch.softmax(att, dim=-1))
+        out[:, :, hs] = (p @ vv).permute(0, 2, 1, 3)
+        del att, p
+    return out
 
 
 @pytest.mark.parametrize("B,S,H,D", [(2, 1024, 16, 72), (1, 256, 2, 72), (3, 128, 4, 72), (1, 729, 3, 72)])
@@ -298,6 +307,74 @@ def test_fmha_paged(cuda):
                    page_table=perm.contiguous())
     ref = ref_attention(q[None], k[None], v[None], True, D ** -0.5)[0]
     assert rel_err(out, ref) < 1.5e-2
+
+
+# ---- the two-tile kernel (fmha2_fwd_kernel: ping-pong softmax warpgroups, O in TMEM with lazy rescale)
+# forced through vila_fmha_cfg(variant=2); the heuristic only picks it once 256-row CTAs fill 148 SMs --
+@pytest.mark.parametrize("B", [1, 8, 64])
+def test_fmha2_noncausal_siglip(cuda, B):
+    from tests.helpers import report_rel
+    ops = _ops()
+    S, H, D = 1024, 16, 72
+    g = torch.Generator(device="cuda").manual_seed(100 + B)
+    qkv = bf(torch.randn(B * S, 3, H, D, device=cuda, generator=g))
+    q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
+    ref = ref_attention(q.view(B, S, H, D), k.view(B, S, H, D), v.view(B, S, H, D), False, D ** -0.5)
+    out2 = ops.fmha(q, k, v, B=B, Sq=S, Sk=S, causal=False, scale=D ** -0.5, variant=2)
+    out1 = ops.fmha(q, k, v, B=B, Sq=S, Sk=S, causal=False, scale=D ** -0.5, variant=1)
+    report_rel(f"fmha2 noncausal d=72 B={B}", out2.view(B, S, H, D), ref, 1.5e-2)
+    report_rel(f"fmha1 noncausal d=72 B={B}", out1.view(B, S, H, D), ref, 1.5e-2)
+    auto = ops.fmha(q, k, v, B=B, Sq=S, Sk=S, causal=False, scale=D ** -0.5)
+    assert torch.equal(auto, out2 if B * H * 4 >= 148 else out1)  # the dispatcher's choice, bit-exact
+
+
+@pytest.mark.parametrize("Sq,Sk", [(4096, 4096), (16448, 16448), (2048, 6000), (129, 129), (300, 812)])
+def test_fmha2_causal_gqa_paged(cuda, Sq, Sk):
+    """causal GQA d=128 over a PAGED, permuted KV pool: full prefill at 4K / 16.4K (64 video frames)
+    and chunked prefill (Sq < Sk)."""
+    from tests.helpers import report_rel
+    ops = _ops()
+    D, Hq, Hkv = 128, 28, 4
+    g = torch.Generator(device="cuda").manual_seed(Sq + Sk)
+    q = bf(torch.randn(Sq, Hq, D, device=cuda, generator=g))
+    k = bf(torch.randn(Sk, Hkv, D, device=cuda, generator=g))
+    v = bf(torch.randn(Sk, Hkv, D, device=cuda, generator=g))
+    n_blk = (Sk + 127) // 128
+    n_pages = n_blk + 5
+    perm = torch.randperm(n_pages, device=cuda, generator=g).to(torch.int32).contiguous()
+    k_pool = bf(torch.randn(n_pages, 128, Hkv, D, device=cuda, generator=g))  # garbage elsewhere
+    v_pool = bf(torch.randn(n_pages, 128, Hkv, D, device=cuda, generator=g))
+    kp = torch.zeros(n_blk * 128, Hkv, D, dtype=torch.bfloat16, device=cuda)
+    vp = torch.zeros_like(kp)
+    kp[:Sk], vp[:Sk] = k, v
+    k_pool[perm[:n_blk].long()] = kp.view(n_blk, 128, Hkv, D)
+    v_pool[perm[:n_blk].long()] = vp.view(n_blk, 128, Hkv, D)
+    ref = ref_attention(q[None], k[None], v[None], True, D ** -0.5)[0]
+    out2 = ops.fmha(q, k_pool, v_pool, B=1, Sq=Sq, Sk=Sk, causal=True, scale=D ** -0.5,
+                    page_table=perm, variant=2)
+    report_rel(f"fmha2 causal GQA paged Sq={Sq} Sk={Sk}", out2, ref, 1.5e-2)
+    out1 = ops.fmha(q, k_pool, v_pool, B=1, Sq=Sq, Sk=Sk, causal=True, scale=D ** -0.5,
+                    page_table=perm, variant=1)
+    report_rel(f"fmha1 causal GQA paged Sq={Sq} Sk={Sk}", out1, ref, 1.5e-2)
+
+
+def test_fmha2_lazy_rescale_growing_maxima(cuda):
+    """Scores that keep growing along the KV axis: every KV block raises the row maxima, some by more
+    than the lazy-rescale threshold (2^8 in the exp2 domain) and some by less -> both the deferred and
+    the forced TMEM-O rescale paths run; d=72 and d=128."""
+    from tests.helpers import report_rel
+    ops = _ops()
+    for (D, H, Hkv, S, causal) in [(128, 8, 2, 2048, True), (72, 16, 16, 1024, False)]:
+        g = torch.Generator(device="cuda").manual_seed(D)
+        q = bf(torch.randn(S, H, D, device=cuda, generator=g))
+        ramp = torch.linspace(0.2, 6.0, S, device=cuda)[:, None, None]       # |k| grows with position
+        k = bf(torch.randn(S, Hkv, D, device=cuda, generator=g) * ramp)
+        v = bf(torch.randn(S, Hkv, D, device=cuda, generator=g))
+        ref = ref_attention(q[None], k[None], v[None], causal, D ** -0.5)[0]
+        for variant in (1, 2):
+            out = ops.fmha(q, k, v, B=1, Sq=S, Sk=S, causal=causal, scale=D ** -0.5, variant=variant)
+            assert torch.isfinite(out.float()).all()
+            report_rel(f"fmha{variant} growing maxima d={D}", out, ref, 1.5e-2)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -460,20 +537,27 @@ def test_gemv_argmax_and_finalize(cuda):
         assert expect == int(torch.argmax(ref))
 
 
-@pytest.mark.parametrize("ctx,splits", [(0, 1), (5, 1), (300, 4), (1000, 8), (130, 16)])
+@pytest.mark.parametrize("ctx,splits", [(0, 1), (5, 1), (300, 4), (1000, 8), (130, 16),
+                                        (16448, 37), (16448, 64), (65814, 37), (65814, 64), (4000, 8)])
 def test_decode_attention(cuda, ctx, splits):
+    """(16448, *) / (65814, *): decode right after a 64-frame / 256-frame video prefill (README.md:69-70
+    publishes decode throughput for exactly that), splits as GraphDecoder.pick_splits chooses them."""
     ops = _ops()
     Hq, Hkv, D = 28, 4, 128
     g = torch.Generator(device="cuda").manual_seed(ctx + splits)
-    n_pages = 16
+    n_pages = max(16, (ctx + 1 + 127) // 128 + 3)
     perm = torch.randperm(n_pages, device=cuda, generator=g).to(torch.int32).contiguous()
     k_hist = bf(torch.randn(ctx, Hkv, D, device=cuda, generator=g))
     v_hist = bf(torch.randn(ctx, Hkv, D, device=cuda, generator=g))
     k_pool = torch.zeros(n_pages, 128, Hkv, D, dtype=torch.bfloat16, device=cuda)
     v_pool = torch.zeros_like(k_pool)
-    for t in range(ctx):
-        k_pool[perm[t // 128], t % 128] = k_hist[t]
-        v_pool[perm[t // 128], t % 128] = v_hist[t]
+    n_blk = (ctx + 127) // 128
+    if n_blk:
+        kp = torch.zeros(n_blk * 128, Hkv, D, dtype=torch.bfloat16, device=cuda)
+        vp = torch.zeros_like(kp)
+        kp[:ctx], vp[:ctx] = k_hist, v_hist
+        k_pool[perm[:n_blk].long()] = kp.view(n_blk, 128, Hkv, D)
+        v_pool[perm[:n_blk].long()] = vp.view(n_blk, 128, Hkv, D)
     qkv = bf(torch.randn((Hq + 2 * Hkv) * D, device=cuda, generator=g))
     pos = torch.tensor([ctx], dtype=torch.int32, device=cuda)
     inv = O.rope_inv_freq(D, 1e6).to(cuda)

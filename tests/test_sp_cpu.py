@@ -98,3 +98,49 @@ def test_inplace_allgather_into_paged_pool_gloo(world):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, S, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def _runner_worker(rank, world, port, n_frames, ret):
+    """host logic of SequenceParallelPrefill that needs a process group but no GPU: ragged frame
+    gather, last-token ownership / broadcast, decode-capable page order."""
+    from types import SimpleNamespace
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        llm = SimpleNamespace(device=torch.device("cpu"), dtype=torch.float32, vocab_size=8)
+        runner = sp.SequenceParallelPrefill(llm)
+        assert runner.world == world and runner.rank == rank
+        g = torch.Generator().manual_seed(1)
+        feats = torch.randn(n_frames, 5, 3, generator=g)            # same on every rank
+        f0, f1 = sp.shard_frames(n_frames, world, rank)
+        got = runner.gather_frame_features(feats[f0:f1].clone(), n_frames)
+        ok = torch.equal(got, feats)
+        S = 2 * world * 128 * 2 - 77
+        plan = sp.make_plan(S, world, rank)
+        hid = torch.zeros(2 * plan.chunk, 4)
+        row = runner.local_row_of(plan, S - 1)
+        if row is not None:
+            hid[row] = torch.tensor([1.0, 2.0, 3.0, 4.0])
+        last = runner.last_token_hidden(hid, plan)
+        ok = ok and torch.equal(last, torch.tensor([1.0, 2.0, 3.0, 4.0]))
+        ok = ok and ((row is not None) == (plan.owner_of(S - 1) == rank))
+        order = sp.sp_cache_page_order(plan, plan.padded_len // 128 + 3)
+        ok = ok and sorted(order) == list(range(len(order))) and order[-3:] == list(range(len(order) - 3, len(order)))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_frames", [(2, 7), (4, 9), (2, 1)])
+def test_runner_host_logic_gloo(world, n_frames):
+    ret = mp.Manager().dict()
+    mp.spawn(_runner_worker, args=(world, _free_port(), n_frames, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_sp_registry_defaults_off():
+    assert not sp.sequence_parallel_enabled()
+    sp.set_sequence_parallel_group(None)
+    assert not sp.sequence_parallel_enabled()  # no process group initialised in this process
+    sp.set_sequence_parallel_group(None, enabled=False)

@@ -75,3 +75,63 @@ def test_sp_prefill_matches_single_gpu(S):
         assert err <= 2 ** -6 * scale, (r, err, scale)
         assert lerr <= 2 ** -5 * max(1.0, scale), (r, lerr)
         assert kv_ok
+
+
+def _api_worker(rank, world, port, n_frames, ret):
+    """sequence parallelism through the PUBLIC API: LlavaLlamaModel.generate / forward with
+    vila_b200.sp.set_sequence_parallel_group — frames sharded over ranks, zigzag SP prefill into the
+    decoder's paged cache, replicated greedy decode."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from vila_b200 import sp
+        from vila_b200.model import LlavaLlamaModel, tiny_test_config
+        cfg = tiny_test_config(projector="mlp_downsample_2x2_fix", llm_layers=3)
+        model = LlavaLlamaModel(cfg, device=f"cuda:{rank}").init_random(5)
+        g = torch.Generator().manual_seed(7)
+        S_img = cfg.vision_tower_cfg.image_size
+        video = torch.randn(n_frames, 3, S_img, S_img, generator=g).to(torch.bfloat16)
+        ids = torch.randint(3, 900, (14,), generator=g).tolist()
+        ids.insert(4, cfg.video_token_id)
+        ids = torch.tensor([ids])
+        # single-GPU answers first (SP off)
+        ref_ids = model.generate(input_ids=ids, media={"video": [video]}, max_new_tokens=12, eos_token_id=None)
+        ref_out = model(input_ids=ids, media={"video": [video]})
+        ref_logits = ref_out.logits[0].float()
+        S = ref_logits.shape[0]
+        sp.set_sequence_parallel_group(None)
+        got_ids = model.generate(input_ids=ids, media={"video": [video]}, max_new_tokens=12, eos_token_id=None)
+        out = model(input_ids=ids, media={"video": [video]})
+        plan = out.sp_plan
+        gathered = [torch.empty_like(out.logits[0]) for _ in range(world)]
+        dist.all_gather(gathered, out.logits[0].contiguous())
+        full = plan.undo_extract_local(torch.stack(gathered))[:S].float()
+        sp.set_sequence_parallel_group(None, enabled=False)
+        again = model.generate(input_ids=ids, media={"video": [video]}, max_new_tokens=12, eos_token_id=None)
+        err = (full - ref_logits).abs().max().item()
+        scale = ref_logits.abs().max().item()
+        ret[rank] = (ref_ids[0].tolist(), got_ids[0].tolist(), again[0].tolist(), err, scale, S, plan.padded_len)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [7, 40])  # 7: ragged frame shards (4 + 3)
+def test_sp_public_api_generate_and_forward(n_frames):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_api_worker, args=(world, _free_port(), n_frames, ret), nprocs=world, join=True)
+    for r in range(world):
+        ref_ids, got_ids, again, err, scale, S, padded = ret[r]
+        assert S == n_frames * 17 + 14 and padded % 512 == 0
+        assert again == ref_ids                      # SP off again -> same single-GPU path
+        assert err <= 2 ** -5 * max(1.0, scale), (r, err, scale)
+        # same ids on every rank; equal to the single-GPU ids up to a bf16-level tie
+        assert got_ids == ret[0][1]
+        n_same = next((i for i, (a, b) in enumerate(zip(got_ids, ref_ids)) if a != b), len(ref_ids))
+        assert n_same >= 1, (got_ids, ref_ids)

@@ -72,6 +72,7 @@ SIGNATURES = {
     "vila_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
     "vila_rmsnorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
     "vila_fmha": [C.POINTER(FmhaParams), c_void_p],
+    "vila_fmha_cfg": [c_int, C.POINTER(FmhaParams), c_void_p],
     "vila_patch_im2col": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "vila_space_to_depth": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "vila_s2_merge": [c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(c_int), C.POINTER(c_int),

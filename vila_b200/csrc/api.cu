@@ -97,8 +97,7 @@ int vila_rmsnorm(void* x_inout, const void* residual_add, const void* weight, vo
                           st(stream));
 }
 
-int vila_fmha(const vila_fmha_params* p, void* stream) {
-  VB_REQUIRE_DEVICE();
+static vb::FmhaParams to_fmha(const vila_fmha_params* p) {
   vb::FmhaParams q;
   q.q = cb(p->q);
   q.q_tok_stride = p->q_tok_stride;
@@ -117,7 +116,17 @@ int vila_fmha(const vila_fmha_params* p, void* stream) {
   q.B = p->B; q.Sq = p->Sq; q.Sk = p->Sk; q.Hq = p->Hq; q.Hkv = p->Hkv; q.D = p->D;
   q.causal = p->causal;
   q.scale = p->scale;
-  return vb::fmha_prefill(q, st(stream));
+  return q;
+}
+
+int vila_fmha(const vila_fmha_params* p, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::fmha_prefill(to_fmha(p), st(stream));
+}
+
+int vila_fmha_cfg(int variant, const vila_fmha_params* p, void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::fmha_prefill_cfg(variant, to_fmha(p), st(stream));
 }
 
 int vila_patch_im2col(const void* pixels, void* out, int B, int C, int H, int W, int patch,
@@ -259,18 +268,6 @@ int vila_decode_mega(const vila_mega_params* p, void* stream) {
   m.barrier = p->barrier; m.epoch = p->epoch;
   m.n_tokens = p->n_tokens; m.splits = p->splits;
   m.ks_hidden = m.ks_inter = m.ks_attn = m.xs_bytes = 0;
-  {
-    // profiling aid: VILA_B200_MEGA_DEBUG=<device pointer in hex>,<cta>
-    const char* e = getenv("VILA_B200_MEGA_DEBUG");
-    if (e != nullptr) {
-      unsigned long long ptr = 0;
-      int cta = 0;
-      if (sscanf(e, "%llx,%d", &ptr, &cta) >= 1) {
-        m.debug_times = reinterpret_cast<long long*>(ptr);
-        m.debug_cta = cta;
-      }
-    }
-  }
   return vb::decode_mega(m, st(stream));
 }
 

@@ -84,11 +84,15 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int b = blockIdx.z;
   const int hk = h / (a.Hq / a.Hkv);
   const int off = a.Sk - a.Sq;
+  // causal: CTAs are dispatched in blockIdx order, so map the FIRST CTAs to the LAST (longest-KV)
+  // query tiles — the tail of the grid is then made of the cheapest tiles
+  const int qpair = a.causal ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
+                             : static_cast<int>(blockIdx.x);
 
   int nblk[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
-    const int qt = blockIdx.x * 2 + t;
+    const int qt = qpair * 2 + t;
     int n = 0;
     if (qt * BQ < a.Sq) {
       int kv_end = a.Sk;
@@ -138,7 +142,7 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c)
           tma_load_4d(q_s + t * C::kTileBytes + c * C::kChunkBytes, &tm_q, &q_full[t], c * CW, h,
-                      b * a.Sq + (blockIdx.x * 2 + t) * BQ, 0);
+                      b * a.Sq + (qpair * 2 + t) * BQ, 0);
       }
       for (int i = 0; i < 2 * nmax; ++i) {  // item 2j = K(j), 2j+1 = V(j)
         const int j = i >> 1;
@@ -232,7 +236,7 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // ===================== softmax warpgroups =====================
     const int t = warp >> 2;                 // query tile of this warpgroup
     const int row = threadIdx.x & 127;
-    const int qt = blockIdx.x * 2 + t;
+    const int qt = qpair * 2 + t;
     const int q_idx = qt * BQ + row;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int n = nblk[t];

@@ -85,7 +85,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x;
+  // causal: heaviest (last) query tiles first, see fmha2_tcgen05.cu
+  const int qt = a.causal ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)
+                          : static_cast<int>(blockIdx.x);
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int hk = h / (a.Hq / a.Hkv);
@@ -391,7 +393,12 @@ int launch_fmha(const FmhaParams& p, cudaStream_t stream) {
 
 }  // namespace
 
-int fmha_prefill(const FmhaParams& p, cudaStream_t stream) {
+int fmha_prefill(const FmhaParams& p, cudaStream_t stream) { return fmha_prefill_cfg(0, p, stream); }
+
+// variant: 0 = size heuristic, 1 = force the one-tile-per-CTA kernel, 2 = force the two-tile kernel
+// (falls through to v1 only when v2 does not cover the head dim / Sq <= 128).
+int fmha_prefill_cfg(int variant, const FmhaParams& p, cudaStream_t stream) {
+  VB_CHECK(variant >= 0 && variant <= 2, "fmha: unknown variant %d", variant);
   VB_CHECK(p.B > 0 && p.Sq > 0 && p.Sk > 0, "fmha: empty problem");
   VB_CHECK(p.Hq % p.Hkv == 0, "fmha: Hq (%d) must be a multiple of Hkv (%d)", p.Hq, p.Hkv);
   VB_CHECK(p.D % 8 == 0, "fmha: head dim must be a multiple of 8 (got %d)", p.D);
@@ -403,17 +410,13 @@ int fmha_prefill(const FmhaParams& p, cudaStream_t stream) {
     // v2 (two query tiles per CTA, ping-pong softmax warpgroups) once its 256-row CTAs fill the
     // machine; below that the one-tile-per-CTA kernel has twice the CTAs and the shorter critical
     // path (1 image, 1024 x 16 heads: 22.5 vs 28.2 us; 64 images: 1105 vs 729 us).
-    // VILA_B200_FMHA_V1=1 / =0 forces v1 / v2 (test hook).
-    static int force = -2;
-    if (force == -2) {
-      const char* e = getenv("VILA_B200_FMHA_V1");
-      force = e ? (e[0] == '1' ? 1 : 0) : -1;
-    }
     const long v2_ctas = static_cast<long>((p.Sq + 255) / 256) * p.Hq * p.B;
-    const bool use_v2 = force == 0 ? p.Sq > 128 : (force == 1 ? false : (p.Sq > 128 && v2_ctas >= num_sms()));
+    const bool use_v2 = variant == 2 ? p.Sq > 128
+                                     : (variant == 1 ? false : (p.Sq > 128 && v2_ctas >= num_sms()));
     if (use_v2) {
       const int rc = fmha_prefill_v2(p, stream);
       if (rc >= 0) return rc;
+      VB_CHECK(variant != 2, "fmha: the two-tile kernel does not cover head dim %d", p.D);
     }
   }
   if (p.D == 128) return launch_fmha<128, 64>(p, stream);

@@ -65,6 +65,7 @@ struct FmhaParams {
   float scale;      // softmax scale (1/sqrt(D))
 };
 int fmha_prefill(const FmhaParams& p, cudaStream_t stream);
+int fmha_prefill_cfg(int variant, const FmhaParams& p, cudaStream_t stream);  // 0 auto, 1 one-tile, 2 two-tile
 int fmha_prefill_v2(const FmhaParams& p, cudaStream_t stream);  // -1: shape not handled
 
 // ---- norms ---------------------------------------------------------------------------------------

@@ -43,6 +43,7 @@ class Qwen2Config:
     rms_norm_eps: float = 1e-6
     rope_theta: float = 1000000.0
     max_position_embeddings: int = 32768
+    tie_word_embeddings: bool = False
     model_type: str = "qwen2"
 
     @property
@@ -105,7 +106,8 @@ def nvila_video_8b(**kw) -> LlavaConfig:
 def nvila_lite_3b(**kw) -> LlavaConfig:
     """NVILA-Lite-3B: mlp_downsample_3x3_fix + (assumed) Qwen2.5-3B (scripts/NVILA-Lite/sft.sh)."""
     llm = Qwen2Config(hidden_size=2048, intermediate_size=11008, num_hidden_layers=36,
-                      num_attention_heads=16, num_key_value_heads=2, vocab_size=151936)
+                      num_attention_heads=16, num_key_value_heads=2, vocab_size=151936,
+                      tie_word_embeddings=True)
     return LlavaConfig(llm_cfg=llm, mm_projector_type="mlp_downsample_3x3_fix",
                        image_aspect_ratio="dynamic", **kw)
 

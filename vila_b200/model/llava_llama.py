@@ -133,7 +133,7 @@ class BasicVideoEncoder(BaseEncoder):
 
     def forward(self, videos: List[torch.Tensor], config: Dict[str, Any]) -> List[torch.Tensor]:
         num_frames = [v.shape[0] for v in videos]
-        features = self.parent.encode_images(torch.cat(videos, dim=0))
+        features = self.parent._encode_frames(torch.cat(videos, dim=0))
         features = torch.split(features, num_frames)
         s, e = self.embed_tokens(self.start_tokens), self.embed_tokens(self.end_tokens)
         return [self._process_features(f, s, e) for f in features]
@@ -151,7 +151,7 @@ class TSPVideoEncoder(BasicVideoEncoder):
 
     def forward(self, videos: List[torch.Tensor], config: Dict[str, Any]) -> List[torch.Tensor]:
         num_frames = [v.shape[0] for v in videos]
-        features = self.parent.encode_images(torch.cat(videos, dim=0))
+        features = self.parent._encode_frames(torch.cat(videos, dim=0))
         features = torch.split(features, num_frames)
         s, e = self.embed_tokens(self.start_tokens), self.embed_tokens(self.end_tokens)
         sep = self.embed_tokens(self.sep_tokens)
@@ -199,6 +199,7 @@ class LlavaLlamaModel(nn.Module):
         self.generation_config = None
         self.training = False
         self._vision_graphs = {}
+        self._sp_runner_obj = None
 
     # ---- reference accessors (llava_arch.py:206-226) ----
     def get_llm(self):
@@ -292,6 +293,10 @@ class LlavaLlamaModel(nn.Module):
         if block_sizes is None:
             block_sizes = [None] * len(images)
         tower, proj = self.get_vision_tower(), self.get_mm_projector()
+        # pixels arrive as fp32 (media._to_tensor), fp16 (the reference calls .half(),
+        # llava_arch.py:864) or bf16; every kernel below computes in the model dtype, and the
+        # features stay in it (the reference casts them back only to feed them to a same-dtype LLM)
+        images = images.to(device=self.device, dtype=self.dtype, non_blocking=True)
         if not getattr(self.config, "dynamic_s2", False):
             # tower + projector replayed from a CUDA graph cached per input shape (~190 launches per
             # call otherwise issued one by one from Python)
@@ -347,6 +352,40 @@ class LlavaLlamaModel(nn.Module):
         if all(o.shape[0] == outs[0].shape[0] for o in outs):
             return torch.stack(outs, dim=0)
         return outs
+
+    # ---- sequence parallelism (LongVILA; reference: llava/train/sequence_parallel/*, the SP branch of
+    # repack_multimodal_data llava_arch.py:561-742, eval_vision_niah.py:83-140) ----
+    def _sp_runner(self):
+        """The SequenceParallelPrefill of the registered group, or None when SP is off
+        (vila_b200.sp.set_sequence_parallel_group)."""
+        from .. import sp
+        if not sp.sequence_parallel_enabled():
+            return None
+        grp = sp.sequence_parallel_group()
+        if self._sp_runner_obj is None or self._sp_runner_obj.group is not grp:
+            self._sp_runner_obj = sp.SequenceParallelPrefill(self.llm, grp)
+        return self._sp_runner_obj
+
+    @torch.inference_mode()
+    def _encode_frames(self, frames: torch.Tensor, batch: int = 32) -> torch.Tensor:
+        """encode_images over video frames.  Under sequence parallelism the frames are sharded in
+        contiguous ranges over the ranks (the reference's collator does the same split,
+        sequence_parallel/input_utils.py:26-30): each rank copies / encodes only its own frames and
+        one all-gather assembles [F, N, hidden] everywhere (no collective inside the tower)."""
+        runner = self._sp_runner()
+        if runner is None:
+            return self.encode_images(frames)
+        from .. import sp
+        F_all = frames.shape[0]
+        f0, f1 = sp.shard_frames(F_all, runner.world, runner.rank)
+        feats = [self.encode_images(frames[i:min(i + batch, f1)]).clone() for i in range(f0, f1, batch)]
+        if feats:
+            local = torch.cat(feats, dim=0)
+        else:
+            r = self.mm_projector.downsample_rate
+            g = (self.config.vision_tower_cfg.grid + r - 1) // r
+            local = torch.empty(0, g * g, self.config.hidden_size, dtype=self.dtype, device=self.device)
+        return runner.gather_frame_features(local, F_all)
 
     # ---- _embed (llava_arch.py:412-490) ----
     def __embed_media_tokens(self, media, media_config):
@@ -436,6 +475,9 @@ class LlavaLlamaModel(nn.Module):
         if inputs_embeds is None:
             inputs_embeds, labels, attention_mask = self._embed(input_ids, media, media_config, labels,
                                                                 attention_mask)
+        runner = self._sp_runner()
+        if runner is not None and past_key_values is None:
+            return self._forward_sequence_parallel(runner, inputs_embeds, attention_mask, labels, dpo_forward)
         if force_packing:
             raise NotImplementedError("sequence packing is a training-time path (SURVEY §8 a14)")
         outputs = self.llm(inputs_embeds=inputs_embeds, attention_mask=attention_mask,
@@ -443,6 +485,34 @@ class LlavaLlamaModel(nn.Module):
         if dpo_forward:
             return outputs.logits, labels
         return outputs
+
+    @torch.inference_mode()
+    def _forward_sequence_parallel(self, runner, inputs_embeds, attention_mask, labels, dpo_forward):
+        """forward under sequence parallelism: like the reference's SP branch every rank returns the
+        logits (and labels) of ITS shard of the sequence — here the two zigzag chunks of
+        sp.ZigzagPlan — plus `sp_plan` so callers can `undo_extract_local` / find the last token
+        (eval_vision_niah.py:121-133)."""
+        from .. import sp
+        assert inputs_embeds.shape[0] == 1, "sequence parallelism shards ONE long sequence"
+        emb = inputs_embeds[0]
+        if attention_mask is not None:
+            emb = emb[attention_mask[0].to(torch.bool)]
+        S = emb.shape[0]
+        plan = sp.make_plan(S, runner.world, runner.rank)
+        padded = emb.new_zeros((plan.padded_len, emb.shape[1]))
+        padded[:S] = emb
+        hid_local, _ = runner.prefill_hidden(plan.extract_local(padded), plan)
+        logits = self.llm.logits_from_hidden(hid_local)[None]
+        local_labels = None
+        if labels is not None:
+            lab = labels[0][attention_mask[0].to(torch.bool)] if attention_mask is not None else labels[0]
+            lab_p = torch.full((plan.padded_len,), IGNORE_INDEX, dtype=lab.dtype, device=lab.device)
+            lab_p[:S] = lab
+            local_labels = plan.extract_local(lab_p)[None]
+        if dpo_forward:
+            return logits, local_labels
+        return SimpleNamespace(logits=logits, loss=None, past_key_values=None, labels=local_labels,
+                               sp_plan=plan)
 
     __call__ = forward
 
@@ -452,10 +522,13 @@ class LlavaLlamaModel(nn.Module):
                  **generation_kwargs):
         inputs_embeds, _, attention_mask = self._embed(input_ids, media, media_config, None,
                                                        attention_mask)
-        if "generation_config" not in generation_kwargs and "max_new_tokens" not in generation_kwargs:
+        # HF merges the model's generation_config under explicit kwargs; ours comes from the tokenizer
+        # (default_generation_config, llava_arch.py:950-963) so eos / pad are known even when the
+        # caller only passes max_new_tokens (explicit kwargs, e.g. eos_token_id=None, still win)
+        if "generation_config" not in generation_kwargs:
             generation_kwargs["generation_config"] = self.default_generation_config
         return self.llm.generate(inputs_embeds=inputs_embeds, attention_mask=attention_mask,
-                                 **generation_kwargs)
+                                 sp_runner=self._sp_runner(), **generation_kwargs)
 
     @property
     def default_generation_config(self):

@@ -85,11 +85,21 @@ def load_pretrained(model_path: str, device="cuda") -> LlavaLlamaModel:
         except Exception:
             tok = None
     model = LlavaLlamaModel(cfg, device=device, tokenizer=tok)
+    gc_file = d / "llm" / "generation_config.json"
+    if gc_file.exists():  # HF from_pretrained populates model.generation_config from this file
+        from types import SimpleNamespace
+        gc = {"max_length": 20, "max_new_tokens": None, "do_sample": False, "pad_token_id": None,
+              "bos_token_id": None, "eos_token_id": None, "temperature": 1.0, "top_p": 1.0, "top_k": 0}
+        gc.update({k: v for k, v in json.loads(gc_file.read_text()).items() if k in gc})
+        model.generation_config = SimpleNamespace(**gc)
+        model.llm.generation_config = model.generation_config
     sd = {}
     sd.update({"llm." + k: v for k, v in _load_dir_tensors(d / "llm").items()})
     sd.update({"vision_tower.vision_tower." + k: v for k, v in _load_dir_tensors(d / "vision_tower").items()})
     sd.update({"mm_projector." + k: v for k, v in _load_dir_tensors(d / "mm_projector").items()})
     own = model.state_dict()
+    if cfg.llm_cfg.tie_word_embeddings and "llm.lm_head.weight" not in sd:
+        sd["llm.lm_head.weight"] = sd["llm.model.embed_tokens.weight"]  # tied checkpoints ship one copy
     missing = [k for k in own if k not in sd]
     if missing:
         raise RuntimeError(f"checkpoint {model_path} lacks {len(missing)} tensors, e.g. {missing[:4]}")

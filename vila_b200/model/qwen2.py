@@ -25,6 +25,7 @@ from .. import ops
 from .configuration import Qwen2Config
 
 PAGE = 128
+_UNSET = object()
 
 
 def _param(t):
@@ -116,8 +117,12 @@ class Qwen2ForCausalLM(nn.Module):
         m.norm.weight = _param(torch.empty(cfg.hidden_size, device=device, dtype=dtype))
         self.model = m
         self.lm_head = _Holder()
-        self.lm_head.weight = _param(torch.empty(cfg.vocab_size, cfg.hidden_size, device=device,
-                                                 dtype=dtype))
+        if getattr(cfg, "tie_word_embeddings", False):
+            # Qwen2.5-0.5B/1.5B/3B tie lm_head to the input embedding: ONE tensor, like HF tie_weights
+            self.lm_head.weight = m.embed_tokens.weight
+        else:
+            self.lm_head.weight = _param(torch.empty(cfg.vocab_size, cfg.hidden_size, device=device,
+                                                     dtype=dtype))
         # HF Qwen2RotaryEmbedding: inv_freq = 1 / theta^(arange(0, D, 2) / D), fp32
         D = cfg.head_dim
         self.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))
@@ -151,10 +156,17 @@ class Qwen2ForCausalLM(nn.Module):
         per-kernel host work, so PDL overlap is not throttled by Python.  The returned tensor is a
         static graph output: consume it before the next call with the same key."""
         S = inputs_embeds.shape[0]
-        if cache.length != 0 or S == 0:
+        if cache.length != 0 or S == 0 or S > 4096:
+            # long prompts (video) are not launch-bound, and a captured graph would pin GBs of
+            # intermediates in its private pool
             return self.prefill_hidden(inputs_embeds, cache)
-        key = (S, cache.pool.data_ptr(), cache.page_table.data_ptr())
+        # the captured graph bakes in per-layer K/V pointers (pool[li, 0/1]: they depend on n_pages)
+        # and the page table: key on the pool geometry too and keep the cache alive in the entry so
+        # the allocator cannot hand the same address to a differently-shaped pool
+        key = (S, cache.pool.data_ptr(), tuple(cache.pool.shape), cache.page_table.data_ptr())
         ent = self._prefill_graphs.get(key)
+        if ent is not None and ent[3] is not cache:
+            ent = None  # a different cache object at a recycled address: re-capture
         if ent is None:
             if len(self._prefill_graphs) >= 8:  # bound the private pools held by cached graphs
                 self._prefill_graphs.pop(next(iter(self._prefill_graphs)))
@@ -167,9 +179,9 @@ class Qwen2ForCausalLM(nn.Module):
             with torch.cuda.graph(g):
                 static_out = self.prefill_hidden(static_in, cache)
             cache.length = 0
-            ent = (g, static_in, static_out)
+            ent = (g, static_in, static_out, cache)
             self._prefill_graphs[key] = ent
-        g, static_in, static_out = ent
+        g, static_in, static_out, _ = ent
         static_in.copy_(inputs_embeds)
         g.replay()
         cache.length = S
@@ -268,10 +280,11 @@ class Qwen2ForCausalLM(nn.Module):
     @torch.inference_mode()
     def generate(self, inputs_embeds: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                  generation_config=None, max_new_tokens: Optional[int] = None, do_sample=None,
-                 eos_token_id=None, pad_token_id=None, logits_processor=None, temperature=None,
-                 top_p=None, top_k=None, **kw) -> torch.Tensor:
+                 eos_token_id=_UNSET, pad_token_id=None, logits_processor=None, temperature=None,
+                 top_p=None, top_k=None, sp_runner=None, **kw) -> torch.Tensor:
         """HF GenerationMixin.generate(inputs_embeds=...) contract: returns ONLY the new ids
-        [B, <=max_new_tokens] (pad-filled after EOS)."""
+        [B, <=max_new_tokens] (pad-filled after EOS).  sp_runner: a sp.SequenceParallelPrefill ->
+        the prompt is prefilled sequence-parallel across its group (greedy, batch size 1)."""
         gc = generation_config or self.generation_config
 
         def pick(name, given, default):
@@ -285,7 +298,9 @@ class Qwen2ForCausalLM(nn.Module):
             max_len = pick("max_length", None, 20)
             max_new = max(1, max_len - inputs_embeds.shape[-2])
         sample = bool(pick("do_sample", do_sample, False))
-        eos = pick("eos_token_id", eos_token_id, None)
+        # eos_token_id=None passed explicitly means "never stop" (benchmarks, parity tests)
+        eos = None if eos_token_id is None else pick(
+            "eos_token_id", None if eos_token_id is _UNSET else eos_token_id, None)
         eos_ids = [] if eos is None else ([eos] if isinstance(eos, int) else list(eos))
         pad = pick("pad_token_id", pad_token_id, eos_ids[0] if eos_ids else 0)
         if inputs_embeds.dim() == 2:
@@ -295,12 +310,14 @@ class Qwen2ForCausalLM(nn.Module):
             emb = inputs_embeds[b]
             if attention_mask is not None:
                 emb = emb[attention_mask[b].to(torch.bool)]
+            if sp_runner is not None and (sample or logits_processor or inputs_embeds.shape[0] != 1):
+                raise NotImplementedError("sequence-parallel generate: greedy decoding, batch size 1")
             if sample or logits_processor:
                 ids = self._generate_eager(emb, max_new, eos_ids, sample, logits_processor,
                                            pick("temperature", temperature, 1.0),
                                            pick("top_p", top_p, 1.0), pick("top_k", top_k, 0))
             else:
-                ids = self._generate_greedy(emb, max_new, eos_ids)
+                ids = self._generate_greedy(emb, max_new, eos_ids, sp_runner=sp_runner)
             outs.append(ids)
         n = max(len(o) for o in outs)
         res = torch.full((len(outs), n), pad, dtype=torch.long, device=self.device)
@@ -309,12 +326,29 @@ class Qwen2ForCausalLM(nn.Module):
         return res
 
     def _generate_greedy(self, emb: torch.Tensor, max_new: int, eos_ids: List[int],
-                         check_every: int = 16) -> List[int]:
+                         check_every: int = 16, sp_runner=None) -> List[int]:
         S = emb.shape[0]
         dec = self.decoder(max_new)
-        cache = dec.cache_for(S + max_new)
-        hid = self.prefill_hidden_graphed(emb, cache)
-        dec.start(hid[-1], cache)
+        if sp_runner is not None:
+            # sequence-parallel prefill (vila_b200/sp.py): every rank ends with the COMPLETE K/V in
+            # its paged pool (in-place all-gather), so the greedy decode then runs replicated on
+            # every rank from the same last hidden state -> identical ids everywhere
+            from .. import sp
+            plan = sp.make_plan(S, sp_runner.world, sp_runner.rank)
+            cache = dec.cache_for(plan.padded_len + max_new,
+                                  page_order_fn=lambda n: sp.sp_cache_page_order(plan, n),
+                                  order_key=("sp", plan.world, plan.rank, plan.padded_len))
+            padded = emb.new_zeros((plan.padded_len, emb.shape[1]))
+            padded[:S] = emb
+            hid_local, _ = sp_runner.prefill_hidden(plan.extract_local(padded), plan, pool=cache.pool)
+            cache.length = S
+            last = sp_runner.last_token_hidden(hid_local, plan)
+            self.last_prefill_hidden = last.clone()
+            dec.start(last, cache)
+        else:
+            cache = dec.cache_for(S + max_new)
+            hid = self.prefill_hidden_graphed(emb, cache)
+            dec.start(hid[-1], cache)
         done = 0
         ids: List[int] = []
         while done < max_new:
@@ -372,13 +406,16 @@ class GraphDecoder:
     graph and replayed without host synchronisation (the reference runs ~400 launches and one D2H
     stopping-criteria sync per token, SURVEY §3.1 HOT LOOP C)."""
 
-    def __init__(self, llm: Qwen2ForCausalLM, max_new: int, num_splits: int = 8):
+    MAX_SPLITS = 64
+
+    def __init__(self, llm: Qwen2ForCausalLM, max_new: int, num_splits: Optional[int] = None):
         self.llm = llm
         cfg = llm.config
         dev, dt = llm.device, llm.dtype
         self.max_new = max_new
         Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
-        self.num_splits = num_splits
+        self._fixed_splits = num_splits
+        self.num_splits = num_splits or 8
         self.x = torch.zeros(cfg.hidden_size, device=dev, dtype=dt)
         self.qkv = torch.zeros((Hq + 2 * Hkv) * D, device=dev, dtype=dt)
         self.attn = torch.zeros(Hq * D, device=dev, dtype=dt)
@@ -388,19 +425,44 @@ class GraphDecoder:
         self.hist = torch.zeros(max_new + 8, device=dev, dtype=torch.int32)
         self.step = torch.zeros(1, device=dev, dtype=torch.int32)
         self.position = torch.zeros(1, device=dev, dtype=torch.int32)
-        self.ws = torch.zeros(Hkv * num_splits * (Hq // Hkv) * (D + 2), device=dev,
+        self.ws = torch.zeros(Hkv * self.MAX_SPLITS * (Hq // Hkv) * (D + 2), device=dev,
                               dtype=torch.float32)
         self.counters = torch.zeros(Hkv, device=dev, dtype=torch.int32)
         self.cache: Optional[PagedKVCache] = None
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graphs = {}  # num_splits -> captured CUDA graph of one decode step (for self.cache)
         self.launches_per_step = 5 * cfg.num_hidden_layers + 2
 
-    def cache_for(self, tokens: int) -> PagedKVCache:
-        """(Re)use a cache big enough; the graph bakes in the pool / page-table pointers."""
-        if self.cache is None or self.cache.max_tokens < tokens:
-            self.cache = self.llm.new_cache(max(tokens, 1024))
-            self.graph = None
+    @property
+    def graph(self):
+        return self.graphs.get(self.num_splits)
+
+    def pick_splits(self, ctx: int) -> int:
+        """KV splits per KV head for a context of `ctx` tokens.  Short contexts: 8 splits = one
+        thread-block cluster per KV head (DSMEM combine, lowest latency).  Long contexts (video:
+        16K-66K tokens = 34-135 MB of K/V per layer) are a bandwidth problem: spread the stream over
+        every SM (Hkv * splits >= #SMs; combine through the fp32 workspace, last CTA reduces)."""
+        if self._fixed_splits:
+            return self._fixed_splits
+        Hkv = self.llm.config.num_key_value_heads
+        if ctx <= 2048:
+            return 8
+        sms = torch.cuda.get_device_properties(self.llm.device).multi_processor_count
+        per_head = max(8, min(self.MAX_SPLITS, (2 * sms) // Hkv))   # two CTAs per SM
+        return int(min(per_head, max(8, (ctx + 255) // 256)))
+
+    def cache_for(self, tokens: int, page_order_fn=None, order_key=None) -> PagedKVCache:
+        """(Re)use a cache big enough; the graphs bake in the pool / page-table pointers.
+        page_order_fn(n_pages) -> physical page of each logical 128-token block (sequence-parallel
+        prefill: the zigzag all-gather layout, sp.sp_cache_page_order); order_key identifies it."""
+        if (self.cache is None or self.cache.max_tokens < tokens
+                or getattr(self, "_order_key", None) != order_key):
+            n_tok = max(tokens, 1024)
+            order = page_order_fn((n_tok + PAGE - 1) // PAGE) if page_order_fn is not None else None
+            self.cache = self.llm.new_cache(n_tok, order)
+            self._order_key = order_key
+            self.graphs = {}
         self.cache.length = 0
+        self.num_splits = self.pick_splits(tokens)
         return self.cache
 
     def _step(self):
@@ -443,14 +505,15 @@ class GraphDecoder:
             self._started = 2
         if n <= 0:
             return
-        if self.graph is None:
+        g = self.graphs.get(self.num_splits)
+        if g is None:
             # warm-up launch outside capture is not allowed to change state: capture directly
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._step()
-            self.graph = g
+            self.graphs[self.num_splits] = g
         for _ in range(n):
-            self.graph.replay()
+            g.replay()
         self.cache.length += n
 
     def tokens(self, n: int) -> List[int]:
@@ -463,7 +526,7 @@ class MegaDecoder(GraphDecoder):
     ahead across layer / token boundaries, grid barriers between phases."""
 
     def __init__(self, llm: Qwen2ForCausalLM, max_new: int, num_splits: int = 8):
-        super().__init__(llm, max_new, num_splits)
+        super().__init__(llm, max_new, num_splits)  # the mega-kernel keeps 8 cluster-free splits
         cfg = llm.config
         dev = llm.device
         Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim

@@ -104,8 +104,9 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float,
 
 def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, Sq: int, Sk: int,
          causal: bool, scale: float, out: Optional[torch.Tensor] = None,
-         page_table: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q [B*Sq, Hq, D] view; k/v either [B*Sk, Hkv, D] views or paged pools [P, 128, Hkv, D]."""
+         page_table: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
+    """q [B*Sq, Hq, D] view; k/v either [B*Sk, Hkv, D] views or paged pools [P, 128, Hkv, D].
+    variant (test hook, vila_fmha_cfg): 0 heuristic, 1 one-tile kernel, 2 two-tile kernel."""
     _chk(q, "q"); _chk(k, "k"); _chk(v, "v")
     assert q.dim() == 3 and q.stride(2) == 1
     Hq, D = q.shape[1], q.shape[2]
@@ -136,7 +137,10 @@ def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, Sq: int, 
     p.B, p.Sq, p.Sk, p.Hq, p.Hkv, p.D = B, Sq, Sk, Hq, Hkv, D
     p.causal = 1 if causal else 0
     p.scale = scale
-    check(_lib.load().vila_fmha(C.byref(p), _stream()), "vila_fmha")
+    if variant == 0:
+        check(_lib.load().vila_fmha(C.byref(p), _stream()), "vila_fmha")
+    else:
+        check(_lib.load().vila_fmha_cfg(variant, C.byref(p), _stream()), "vila_fmha_cfg")
     return out
 
 

@@ -83,6 +83,39 @@ def make_plan(seq_len: int, world: int, rank: int) -> ZigzagPlan:
     return ZigzagPlan(world, rank, seq_len, padded, padded // (2 * world))
 
 
+# ---- process-group registry (the reference's PROCESS_GROUP_MANAGER, llava/train/sequence_parallel/
+# globals.py:84-149, reduced to the one group the inference path needs) ---------------------------
+_SP_GROUP = None
+_SP_ENABLED = False
+
+
+def set_sequence_parallel_group(group=None, enabled: bool = True) -> None:
+    """Enable sequence parallelism for LlavaLlamaModel.forward / generate over `group` (None = the
+    default torch.distributed group).  Mirrors `set_pg_manager(sp_degree, ...)` of the reference."""
+    global _SP_GROUP, _SP_ENABLED
+    _SP_GROUP, _SP_ENABLED = group, enabled
+
+
+def sequence_parallel_group():
+    return _SP_GROUP
+
+
+def sequence_parallel_enabled() -> bool:
+    if not _SP_ENABLED:
+        return False
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized()
+
+
+def sp_cache_page_order(plan: "ZigzagPlan", n_pages: int) -> List[int]:
+    """Page order of a decode-capable KV cache whose first padded_len/128 pages are the zigzag
+    all-gather layout and whose remaining pages (tokens generated past the padded prompt) are
+    identity-mapped."""
+    base = plan.page_table().tolist()
+    assert n_pages >= len(base)
+    return base + list(range(len(base), n_pages))
+
+
 def shard_frames(n_frames: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous frame range per rank for the vision tower (extract_local_from_list,
     llava/train/sequence_parallel/input_utils.py:26-30)."""
@@ -99,18 +132,40 @@ class SequenceParallelPrefill:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.comm_stream = torch.cuda.Stream()
+        self._comm_stream = None  # created on first use (the host logic is testable without a GPU)
+        self._plan_cache = {}
 
-    def new_pool(self, plan: ZigzagPlan):
+    @property
+    def comm_stream(self):
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.llm.device)
+        return self._comm_stream
+
+    def new_pool(self, plan: ZigzagPlan, extra_tokens: int = 0):
         cfg = self.llm.config
-        n_pages = plan.padded_len // PAGE
+        n_pages = plan.padded_len // PAGE + (extra_tokens + PAGE - 1) // PAGE
         return torch.zeros(cfg.num_hidden_layers, 2, n_pages, PAGE, cfg.num_key_value_heads,
                            cfg.head_dim, device=self.llm.device, dtype=self.llm.dtype)
+
+    def _device_plan(self, plan: ZigzagPlan):
+        key = (plan.world, plan.rank, plan.padded_len)
+        ent = self._plan_cache.get(key)
+        if ent is None:
+            ent = (plan.page_table().to(self.llm.device), plan.local_positions().to(self.llm.device))
+            self._plan_cache = {key: ent}
+        return ent
 
     @torch.inference_mode()
     def prefill_hidden(self, local_embeds: torch.Tensor, plan: ZigzagPlan, pool=None):
         """local_embeds [2*chunk, hidden] (rows of this rank's two zigzag chunks, padded rows zero).
-        Returns this rank's final hidden states [2*chunk, hidden] (pre final-norm) and the pool."""
+        Returns this rank's final hidden states [2*chunk, hidden] (pre final-norm) and the pool
+        [L, 2, >= padded_len/128 pages, 128, Hkv, D]; its first padded_len/128 pages are the gathered
+        zigzag layout (extra pages, if any, are left for tokens decoded later).
+
+        Per layer: q/k/v GEMM -> RoPE(global positions) + K/V rows into this rank's pool region ->
+        the K/V all-gather is issued on `comm_stream`; rank 0's first chunk attends only to its own
+        pages and runs under the exchange, every other chunk waits for the gathered K/V.  The
+        exchange moves 118 MB per GPU per layer at S = 65.8K over NVSwitch (~0.2 ms of a ~9 ms layer)."""
         import torch.distributed as dist
         from . import ops
         llm, cfg = self.llm, self.llm.config
@@ -118,11 +173,12 @@ class SequenceParallelPrefill:
         c, cp = plan.chunk, plan.chunk_pages
         assert local_embeds.shape[0] == 2 * c
         pool = pool if pool is not None else self.new_pool(plan)
-        page_table = plan.page_table().to(llm.device)
-        positions = plan.local_positions().to(llm.device)
+        zz_pages = plan.padded_len // PAGE
+        page_table, positions = self._device_plan(plan)
         (a0, a1), (b0, b1) = plan.local_chunks()
         x = local_embeds.to(llm.dtype).contiguous().clone()
         n_local_pages = 2 * cp
+        compute = torch.cuda.current_stream()
         for li, layer in enumerate(llm.model.layers):
             h = ops.rmsnorm(x, layer.input_layernorm.weight, cfg.rms_norm_eps)
             qkv = ops.linear(h, layer._qkv_w, layer._qkv_b, static_w=True)
@@ -132,16 +188,29 @@ class SequenceParallelPrefill:
                                page_table, a0)
             ops.rope_kv_append(qkv[c:], positions[c:], Hq, Hkv, D, llm.inv_freq, kpool, vpool,
                                page_table, b0)
-            if self.world > 1:
-                # ONE in-place all-gather per tensor replaces the ring's P-1 P2P rounds
-                lo = self.rank * n_local_pages
-                for t in (kpool, vpool):
-                    dist.all_gather_into_tensor(t.view(-1), t[lo:lo + n_local_pages].view(-1),
-                                                group=self.group)
             q = qkv.view(2 * c, Hq + 2 * Hkv, D)[:, :Hq]
             attn = torch.empty(2 * c, Hq, D, dtype=llm.dtype, device=llm.device)
-            ops.fmha(q[:c], kpool, vpool, B=1, Sq=c, Sk=a1, causal=True, scale=D ** -0.5,
-                     page_table=page_table, out=attn[:c])
+            if self.world > 1:
+                # ONE in-place all-gather per tensor replaces the ring's P-1 P2P rounds; it runs on
+                # the communication stream, ordered after this layer's K/V writes
+                self.comm_stream.wait_stream(compute)
+                lo = self.rank * n_local_pages
+                with torch.cuda.stream(self.comm_stream):
+                    for t in (kpool, vpool):
+                        dist.all_gather_into_tensor(t[:zz_pages].view(-1),
+                                                    t[lo:lo + n_local_pages].view(-1), group=self.group)
+                if self.rank == 0:
+                    # chunk 0 attends to global tokens [0, chunk) only = rank 0's own slot-0 pages:
+                    # no remote K/V needed, so it overlaps the exchange
+                    ops.fmha(q[:c], kpool, vpool, B=1, Sq=c, Sk=a1, causal=True, scale=D ** -0.5,
+                             page_table=page_table, out=attn[:c])
+                compute.wait_stream(self.comm_stream)
+                if self.rank != 0:
+                    ops.fmha(q[:c], kpool, vpool, B=1, Sq=c, Sk=a1, causal=True, scale=D ** -0.5,
+                             page_table=page_table, out=attn[:c])
+            else:
+                ops.fmha(q[:c], kpool, vpool, B=1, Sq=c, Sk=a1, causal=True, scale=D ** -0.5,
+                         page_table=page_table, out=attn[:c])
             ops.fmha(q[c:], kpool, vpool, B=1, Sq=c, Sk=b1, causal=True, scale=D ** -0.5,
                      page_table=page_table, out=attn[c:])
             ops.linear(attn.view(2 * c, Hq * D), layer.self_attn.o_proj.weight, residual=x, out=x, static_w=True)
@@ -149,6 +218,30 @@ class SequenceParallelPrefill:
             a = ops.linear(h, layer._gu_w, swiglu=True, static_w=True)
             ops.linear(a, layer.mlp.down_proj.weight, residual=x, out=x, static_w=True)
         return x, pool
+
+    def local_row_of(self, plan: ZigzagPlan, pos: int) -> Optional[int]:
+        """row index of global position `pos` inside this rank's local rows (None: not owned)."""
+        (a0, a1), (b0, b1) = plan.local_chunks()
+        if a0 <= pos < a1:
+            return pos - a0
+        if b0 <= pos < b1:
+            return plan.chunk + (pos - b0)
+        return None
+
+    @torch.inference_mode()
+    def last_token_hidden(self, hidden_local: torch.Tensor, plan: ZigzagPlan) -> torch.Tensor:
+        """final-layer hidden state [hidden] of the last REAL token on every rank (broadcast from its
+        owner): what seeds the replicated greedy decode (gather of eval_vision_niah.py:121-133)."""
+        import torch.distributed as dist
+        last = plan.seq_len - 1
+        owner = plan.owner_of(last)
+        row = torch.empty(hidden_local.shape[1], dtype=hidden_local.dtype, device=hidden_local.device)
+        if self.rank == owner:
+            row.copy_(hidden_local[self.local_row_of(plan, last)])
+        if self.world > 1:
+            dist.broadcast(row, src=dist.get_global_rank(self.group, owner) if self.group else owner,
+                           group=self.group)
+        return row
 
     @torch.inference_mode()
     def last_token_logits(self, hidden_local: torch.Tensor, plan: ZigzagPlan) -> Optional[torch.Tensor]:
@@ -159,10 +252,24 @@ class SequenceParallelPrefill:
         V = self.llm.vocab_size
         logits = torch.empty(1, V, dtype=self.llm.dtype, device=self.llm.device)
         if self.rank == owner:
-            (a0, a1), (b0, b1) = plan.local_chunks()
-            row = last - a0 if a0 <= last < a1 else plan.chunk + (last - b0)
+            row = self.local_row_of(plan, last)
             logits = self.llm.logits_from_hidden(hidden_local[row:row + 1])
         if self.world > 1:
             dist.broadcast(logits, src=dist.get_global_rank(self.group, owner) if self.group else owner,
                            group=self.group)
         return logits
+
+    @torch.inference_mode()
+    def gather_frame_features(self, local_feats: torch.Tensor, n_frames: int) -> torch.Tensor:
+        """[f_local, N, C] per-rank frame features (contiguous ranges of shard_frames) -> [n_frames, N, C]
+        on every rank; the ragged tail (n_frames % world != 0) is zero-padded for the collective and
+        cut off afterwards (the reference all-reduces zero-padded embeddings, llava_arch.py:591-593)."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return local_feats
+        per = (n_frames + self.world - 1) // self.world
+        padded = local_feats.new_zeros((per,) + tuple(local_feats.shape[1:]))
+        padded[:local_feats.shape[0]] = local_feats
+        allf = local_feats.new_empty((self.world * per,) + tuple(local_feats.shape[1:]))
+        dist.all_gather_into_tensor(allf, padded, group=self.group)
+        return allf[:n_frames]
