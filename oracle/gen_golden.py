@@ -197,10 +197,89 @@ def gen_media():
     torch.save(out, OUT / "media_preprocess.pt")
 
 
+def gen_packing():
+    """reference repack_multimodal_data / _get_unpad_data outputs on the seeded cases of
+    validate_against_reference.packing_cases()."""
+    import types
+    ref_repack, ref_unpad = V.ref_packing_namespace()
+    out = []
+    for emb, mask, labels, pad_mult in V.packing_cases():
+        holder = types.SimpleNamespace(llm=types.SimpleNamespace(pad_token_id=0))
+        if pad_mult:
+            holder.pad_to_multiple_of = pad_mult
+        e, am, pos, lab = ref_repack(holder, emb, mask, None, labels.clone())
+        idx, cu, mx = ref_unpad(am)
+        out.append({"emb": emb, "mask": mask, "labels": labels, "pad_mult": pad_mult,
+                    "out": (e, am, pos, lab), "unpad": (idx, cu, mx)})
+    torch.save(out, OUT / "packing.pt")
+
+
+def gen_dynamic_preprocess():
+    import numpy as np
+    from PIL import Image
+    srcs = V.extract_functions(REF / "llava/mm_utils.py", ["find_closest_aspect_ratio", "dynamic_preprocess", "expand2square"])
+    ns = {"Image": Image}
+    for k in ("find_closest_aspect_ratio", "dynamic_preprocess", "expand2square"):
+        exec(srcs[k], ns)
+    out = []
+    for i, (w, h) in enumerate(MEDIA_SIZES + [(336, 336)]):
+        img = media_test_image(w, h, 200 + i)
+        tiles = ns["dynamic_preprocess"](img, min_num=1, max_num=12, image_size=448)
+        arrs = [np.asarray(t, dtype=np.int64) for t in tiles]
+        sq = np.asarray(ns["expand2square"](img, (127, 127, 127)), dtype=np.int64)
+        out.append({"size": (w, h), "seed": 200 + i, "n_tiles": len(tiles),
+                    "tile_sums": torch.tensor([int(a.sum()) for a in arrs]),
+                    "square_shape": tuple(sq.shape), "square_sum": int(sq.sum())})
+    torch.save(out, OUT / "dynamic_preprocess.pt")
+
+
+def gen_api_signatures():
+    """Public-method signatures of the reference's model classes, extracted from the source with ast
+    (names, order, literal defaults, *args / **kwargs) -> tests/golden/api_signatures.json."""
+    import ast
+    import json
+
+    def sigs(path, cls_names, methods):
+        src = (REF / path).read_text()
+        tree = ast.parse(src)
+        out = {}
+        for node in ast.walk(tree):
+            if isinstance(node, ast.ClassDef) and node.name in cls_names:
+                for fn in node.body:
+                    if isinstance(fn, ast.FunctionDef) and fn.name in methods:
+                        a = fn.args
+                        names = [x.arg for x in a.args]
+                        defaults = [None] * (len(names) - len(a.defaults)) + [
+                            ast.literal_eval(d) if isinstance(d, ast.Constant) else "<expr>" for d in a.defaults]
+                        out.setdefault(node.name, {})[fn.name] = {
+                            "args": names, "defaults": ["<required>" if i < len(names) - len(a.defaults) else defaults[i]
+                                                        for i in range(len(names))],
+                            "vararg": a.vararg.arg if a.vararg else None,
+                            "kwarg": a.kwarg.arg if a.kwarg else None,
+                            "kwonly": [x.arg for x in a.kwonlyargs]}
+        return out
+
+    methods = {"forward", "generate", "generate_content", "encode_images", "_embed", "get_llm", "get_lm_head",
+               "get_vision_tower", "get_mm_projector", "repack_multimodal_data", "get_xgr_logits_processor",
+               "merge_features_for_dynamic_s2"}
+    table = {
+        "llava/model/language_model/llava_llama.py": sigs("llava/model/language_model/llava_llama.py", {"LlavaLlamaModel"}, methods),
+        "llava/model/llava_arch.py": sigs("llava/model/llava_arch.py", {"LlavaMetaModel", "LlavaMetaForCausalLM"}, methods),
+        "llava/remote_code/modeling_vila.py": sigs("llava/remote_code/modeling_vila.py", {"VILAForCausalLM", "VILAPretrainedModel"}, methods),
+        "llava/model/multimodal_projector/base_projector.py": sigs("llava/model/multimodal_projector/base_projector.py", {"MultimodalProjector"}, {"forward"}),
+        "llava/model/encoders/image/basic.py": sigs("llava/model/encoders/image/basic.py", {"BasicImageEncoder"}, {"forward", "embed_tokens", "_process_features"}),
+        "llava/model/encoders/video/basic.py": sigs("llava/model/encoders/video/basic.py", {"BasicVideoEncoder"}, {"forward", "_process_features"}),
+        "llava/model/encoders/video/tsp.py": sigs("llava/model/encoders/video/tsp.py", {"TSPVideoEncoder"}, {"forward", "_process_features"}),
+    }
+    (OUT / "api_signatures.json").write_text(json.dumps(table, indent=1, sort_keys=True))
+
+
 if __name__ == "__main__":
     assert REF.exists(), "needs /root/reference"
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(4)
-    gen_siglip(); gen_projector(); gen_arch_glue(); gen_qwen2(); gen_media()
+    if "--new-only" not in sys.argv:
+        gen_siglip(); gen_projector(); gen_arch_glue(); gen_qwen2(); gen_media()
+    gen_packing(); gen_dynamic_preprocess(); gen_api_signatures()
     for f in sorted(OUT.glob("*.pt")):
         print(f.name, f.stat().st_size)

@@ -329,6 +329,84 @@ def check_qwen2():
         report(f"qwen2 forward logits, positions 60000+ ({attn})", (ref - mine).abs().max().item(), 5e-5)
 
 
+def ref_packing_namespace():
+    """repack_multimodal_data (llava_arch.py:557-800, non-SP branch taken when get_pg_manager() is
+    None) and packing._get_unpad_data, executed from the reference source."""
+    srcs = extract_functions(REF / "llava/model/llava_arch.py", ["repack_multimodal_data"])
+    ns = {"torch": torch, "IGNORE_INDEX": -100, "get_pg_manager": lambda: None, "dist": None}
+    exec(srcs["repack_multimodal_data"], ns)
+    psrc = extract_functions(REF / "llava/model/utils/packing.py", ["_get_unpad_data"])
+    ns2 = {"torch": torch, "F": F, "Tuple": tuple}
+    exec("from typing import Tuple\n" + psrc["_get_unpad_data"], ns2)
+    return ns["repack_multimodal_data"], ns2["_get_unpad_data"]
+
+
+def packing_cases():
+    g = torch.Generator().manual_seed(11)
+    cases = []
+    for lens, L, pad_mult in (([5, 3, 7], 8, None), ([1, 1], 4, None), ([6], 6, None), ([4, 9, 2, 9], 9, 8)):
+        B, H = len(lens), 6
+        emb = torch.randn(B, L, H, generator=g)
+        mask = torch.zeros(B, L, dtype=torch.bool)
+        for k, n in enumerate(lens):
+            mask[k, :n] = True
+        labels = torch.randint(0, 50, (B, L), generator=g)
+        cases.append((emb, mask, labels, pad_mult))
+    return cases
+
+
+def check_packing():
+    from vila_b200.model import packing
+    ref_repack, ref_unpad = ref_packing_namespace()
+    worst = 0.0
+    for emb, mask, labels, pad_mult in packing_cases():
+        holder = types.SimpleNamespace(llm=types.SimpleNamespace(pad_token_id=0))
+        if pad_mult:
+            holder.pad_to_multiple_of = pad_mult
+        ref = ref_repack(holder, emb, mask, None, labels.clone())
+        mine = packing.repack_multimodal_data(emb, mask, None, labels.clone(), pad_mult, 0)
+        for a, b in zip(ref, mine):
+            if a.shape != b.shape or a.dtype != b.dtype:
+                worst = float("inf")
+            else:
+                worst = max(worst, (a.double() - b.double()).abs().max().item())
+        am = ref[1]
+        r_idx, r_cu, r_max = ref_unpad(am)
+        m_idx, m_cu, m_max = packing.get_unpad_data(am)
+        worst = max(worst, float((r_idx - m_idx).abs().max()), float((r_cu - m_cu).abs().max()), abs(r_max - m_max))
+    report("repack_multimodal_data (non-SP) + _get_unpad_data", worst, 0)
+
+
+def check_dynamic_preprocess():
+    """mm_utils.dynamic_preprocess (NVILA-Lite `dynamic`) and expand2square (`pad`) executed from the
+    reference source vs vila_b200.model.media."""
+    import numpy as np
+    from PIL import Image
+    from vila_b200.model import media
+    srcs = extract_functions(REF / "llava/mm_utils.py", ["find_closest_aspect_ratio", "dynamic_preprocess", "expand2square"])
+    ns = {"Image": Image}
+    for k in ("find_closest_aspect_ratio", "dynamic_preprocess", "expand2square"):
+        exec(srcs[k], ns)
+    rng = np.random.RandomState(9)
+    worst, n_bad = 0.0, 0
+    sizes = [(336, 336), (448, 448), (1600, 800), (800, 1600), (333, 1000), (1920, 1080), (97, 131), (3000, 500)]
+    for (w, h) in sizes:
+        img = Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8))
+        for max_num in (12, 6):
+            ref_tiles = ns["dynamic_preprocess"](img, min_num=1, max_num=max_num, image_size=448)
+            my_tiles = media.dynamic_preprocess(img, min_num=1, max_num=max_num, image_size=448)
+            if len(ref_tiles) != len(my_tiles):
+                n_bad += 1
+                continue
+            for a, b in zip(ref_tiles, my_tiles):
+                worst = max(worst, float(np.abs(np.asarray(a, dtype=np.int32) - np.asarray(b, dtype=np.int32)).max()))
+        a = ns["expand2square"](img, (127, 127, 127))
+        b = media.expand2square(img, (127, 127, 127))
+        worst = max(worst, float(np.abs(np.asarray(a, dtype=np.int32) - np.asarray(b, dtype=np.int32)).max()))
+    report(f"dynamic_preprocess tile counts ({len(sizes)} sizes x 2 budgets)", float(n_bad), 0)
+    report("dynamic_preprocess / expand2square pixels", worst, 0)
+
+
 if __name__ == "__main__":
     if not REF.exists():
         print("reference tree not present: nothing to validate against")
@@ -340,6 +418,8 @@ if __name__ == "__main__":
     check_media_preprocess()
     check_pixel_preprocess()
     check_encoders()
+    check_packing()
+    check_dynamic_preprocess()
     check_qwen2()
     print("FAILED:" if FAILED else "ALL OK", FAILED)
     sys.exit(1 if FAILED else 0)

@@ -1,0 +1,176 @@
+"""CPU: the drop-in surface — signatures of every public method against the
+signatures extracted from the reference source (tests/golden/api_signatures.json, made by
+oracle/gen_golden.py with `ast`), the `llava` namespace shim, the CLI plumbing of BASELINE configs[0]
+(`llava.cli.infer` flow up to the model call), packing / dynamic tiling against reference-generated
+fixtures, and the remote-code `generate` semantics."""
+import inspect
+import json
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+# reference class -> our class
+def _classes():
+    from vila_b200 import model as M
+    return {"LlavaLlamaModel": M.LlavaLlamaModel, "LlavaMetaModel": M.LlavaLlamaModel,
+            "LlavaMetaForCausalLM": M.LlavaLlamaModel, "VILAForCausalLM": M.VILAForCausalLM,
+            "VILAPretrainedModel": M.VILAForCausalLM, "MultimodalProjector": M.MultimodalProjector,
+            "BasicImageEncoder": M.BasicImageEncoder, "BasicVideoEncoder": M.BasicVideoEncoder,
+            "TSPVideoEncoder": M.TSPVideoEncoder}
+
+
+def test_public_signatures_accept_every_reference_call():
+    """For every method the reference defines on the path: same name; every reference parameter is
+    either a parameter of ours at the same position with the same literal default, or (for the PS3 /
+    top-down arguments that are out of scope) absorbed by our **kwargs; ours may only ADD defaulted
+    parameters at the end."""
+    table = json.loads((GOLDEN / "api_signatures.json").read_text())
+    classes = _classes()
+    checked = 0
+    for fname, per_class in table.items():
+        for cname, methods in per_class.items():
+            ours_cls = classes[cname]
+            for mname, ref in methods.items():
+                fn = getattr(ours_cls, mname, None)
+                assert fn is not None, f"{cname}.{mname} ({fname}) is missing"
+                if isinstance(inspect.getattr_static(ours_cls, mname), property):
+                    continue
+                sig = inspect.signature(fn)
+                params = list(sig.parameters.values())
+                names = [p.name for p in params if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+                has_kw = any(p.kind == p.VAR_KEYWORD for p in params)
+                for i, (arg, default) in enumerate(zip(ref["args"], ref["defaults"])):
+                    if i < len(names) and names[i] == arg:
+                        ours_default = sig.parameters[arg].default
+                        if default == "<required>":
+                            continue
+                        if default != "<expr>":
+                            assert ours_default == default or ours_default is inspect.Parameter.empty and arg == "self", \
+                                f"{cname}.{mname}({arg}): default {ours_default!r} != reference {default!r}"
+                    else:
+                        assert has_kw and default != "<required>", \
+                            f"{cname}.{mname}: reference parameter #{i} `{arg}` not accepted (ours: {names})"
+                        break  # the remaining reference parameters go to **kwargs as well
+                if ref["kwarg"]:
+                    assert has_kw, f"{cname}.{mname} must accept **{ref['kwarg']}"
+                for p in params[len(ref["args"]):]:
+                    if p.kind == p.POSITIONAL_OR_KEYWORD:
+                        assert p.default is not inspect.Parameter.empty, f"{cname}.{mname}: extra required `{p.name}`"
+                checked += 1
+    assert checked >= 30
+
+
+def test_llava_namespace_shim():
+    import llava
+    import llava.cli.infer
+    import llava.conversation as clib
+    import llava.mm_utils
+    import llava.model
+    import llava.model.builder
+    import llava.model.configuration_llava as cl
+    import llava.remote_code.modeling_vila as rv
+    from vila_b200 import model as M
+    assert llava.model.LlavaLlamaModel is M.LlavaLlamaModel and rv.VILAForCausalLM is M.VILAForCausalLM
+    assert list(inspect.signature(llava.load).parameters) == ["model_path", "model_base", "devices", "kwargs"]
+    assert list(inspect.signature(llava.model.builder.load_pretrained_model).parameters)[:7] == [
+        "model_path", "model_name", "model_base", "load_8bit", "load_4bit", "device_map", "device"]
+    assert llava.Image("a.png").path == "a.png" and issubclass(llava.Video, llava.Media)
+    assert llava.mm_utils.get_model_name_from_path("x/run/checkpoint-7/") == "run_checkpoint-7"
+    rf = cl.ResponseFormat(type="json_schema", json_schema=cl.JsonSchemaResponseFormat(schema="{}"))
+    assert rf.json_schema.schema_ == "{}"
+    assert "auto" in clib.conv_templates and clib.default_conversation.copy().name == "auto"
+
+
+def test_cli_infer_plumbing(monkeypatch, tmp_path):
+    """BASELINE configs[0] plumbing: `llava.cli.infer` with an image + text builds the prompt, maps the
+    flags and calls model.generate_content exactly once (the model itself needs the GPU)."""
+    import llava
+    import llava.cli.infer as infer
+    from PIL import Image as PILImage
+    img = tmp_path / "synthetic.png"
+    PILImage.fromarray(np.random.RandomState(0).randint(0, 256, (336, 336, 3), dtype=np.uint8)).save(img)
+    calls = {}
+
+    class Stub:
+        config = SimpleNamespace(num_video_frames=8, video_max_tiles=1)
+
+        def generate_content(self, prompt, response_format=None):
+            calls["prompt"], calls["rf"] = prompt, response_format
+            return "ok"
+
+    monkeypatch.setattr(llava, "load", lambda path, model_base=None: Stub())
+    out = infer.main(["--model-path", "NVILA-Lite-3B", "--media", str(img), "--text", "Describe.",
+                      "--num_video_frames", "16", "--json-mode"])
+    assert out == "ok" and calls["rf"].type == "json_object"
+    assert isinstance(calls["prompt"][0], llava.Image) and calls["prompt"][1] == "Describe."
+    assert Stub.config.num_video_frames == 16
+    with pytest.raises(ValueError):
+        infer.main(["--model-path", "x", "--media", "file.xyz"])
+
+
+def test_prepare_content_dynamic_tiles_on_host():
+    """NVILA-Lite (`image_aspect_ratio == "dynamic"`): one PIL image -> tiles + thumbnail, the image
+    token repeated once per tile, ids tokenised — all before any GPU work (configs[0]: 336^2 input)."""
+    from PIL import Image as PILImage
+    from vila_b200.model import LlavaLlamaModel, SyntheticTokenizer, nvila_lite_3b
+    cfg = nvila_lite_3b()
+    m = object.__new__(LlavaLlamaModel)
+    torch.nn.Module.__init__(m)
+    m.config, m.tokenizer = cfg, SyntheticTokenizer(cfg)
+    img = PILImage.fromarray(np.random.RandomState(1).randint(0, 256, (336, 336, 3), dtype=np.uint8))
+    ids, media, media_config = m._prepare_content([img, "What is this?"])
+    assert len(media["image"]) == 1 and media["image"][0].shape == (3, 448, 448)   # 1x1 grid: no thumbnail
+    assert int((ids == cfg.image_token_id).sum()) == 1
+    wide = PILImage.fromarray(np.random.RandomState(2).randint(0, 256, (400, 1200, 3), dtype=np.uint8))
+    ids, media, _ = m._prepare_content([wide, "And this?"])
+    assert len(media["image"]) == 4 and int((ids == cfg.image_token_id).sum()) == 4  # 3x1 grid + thumbnail
+    assert all(t.dtype == torch.float32 and float(t.abs().max()) <= 1.0 for t in media["image"])
+
+
+def test_packing_matches_reference_fixture():
+    from vila_b200.model import packing
+    cases = torch.load(GOLDEN / "packing.pt")
+    assert len(cases) == 4
+    for c in cases:
+        got = packing.repack_multimodal_data(c["emb"], c["mask"], None, c["labels"].clone(), c["pad_mult"], 0)
+        for a, b in zip(c["out"], got):
+            assert a.shape == b.shape and a.dtype == b.dtype and torch.equal(a, b)
+        idx, cu, mx = packing.get_unpad_data(got[1])
+        assert torch.equal(idx, c["unpad"][0]) and torch.equal(cu, c["unpad"][1]) and mx == c["unpad"][2]
+
+
+def test_dynamic_preprocess_and_pad_match_reference_fixture():
+    from PIL import Image as PILImage
+    from vila_b200.model import media
+    cases = torch.load(GOLDEN / "dynamic_preprocess.pt")
+    for c in cases:
+        w, h = c["size"]
+        img = PILImage.fromarray(np.random.RandomState(c["seed"]).randint(0, 256, (h, w, 3), dtype=np.uint8))
+        tiles = media.dynamic_preprocess(img, min_num=1, max_num=12, image_size=448)
+        assert len(tiles) == c["n_tiles"]
+        sums = torch.tensor([int(np.asarray(t, dtype=np.int64).sum()) for t in tiles])
+        assert torch.equal(sums, c["tile_sums"])
+        sq = np.asarray(media.expand2square(img, (127, 127, 127)), dtype=np.int64)
+        assert tuple(sq.shape) == c["square_shape"] and int(sq.sum()) == c["square_sum"]
+
+
+def test_remote_code_generate_prepends_prompt_ids(monkeypatch):
+    """modeling_vila.py:1112-1125."""
+    from vila_b200.model import LlavaLlamaModel, VILAForCausalLM
+    new = torch.tensor([[7, 8, 9]])
+    monkeypatch.setattr(LlavaLlamaModel, "generate", lambda self, **kw: new)
+    m = object.__new__(VILAForCausalLM)
+    ids = torch.tensor([[1, 2, 3, 4]])
+    assert VILAForCausalLM.generate.__wrapped__(m, input_ids=ids).tolist() == [[1, 2, 3, 4, 7, 8, 9]] \
+        if hasattr(VILAForCausalLM.generate, "__wrapped__") else True
+    out = VILAForCausalLM.generate(m, input_ids=ids)
+    assert out.tolist() == [[1, 2, 3, 4, 7, 8, 9]]
+    assert VILAForCausalLM.generate(m, input_ids=ids, return_output_ids_only=True).tolist() == [[7, 8, 9]]
+    gc = SimpleNamespace(num_return_sequences=2)
+    monkeypatch.setattr(LlavaLlamaModel, "generate", lambda self, **kw: torch.tensor([[7], [8]]))
+    assert VILAForCausalLM.generate(m, input_ids=ids, generation_config=gc).tolist() == [[1, 2, 3, 4, 7], [1, 2, 3, 4, 8]]

@@ -184,3 +184,88 @@ def test_no_cpu_fallback(cuda):
     from vila_b200 import ops
     with pytest.raises(RuntimeError):
         ops.linear(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+def test_force_packing_matches_unpacked_and_oracle(cuda):
+    """a14: forward(force_packing=True) packs the padded batch into one row (+ dummy token) and runs
+    block-diagonal causal attention; every packed row must carry the logits the same token gets in the
+    ordinary padded-batch forward, and the oracle's per-sequence logits."""
+    from vila_b200.model import tiny_test_config
+    cfg = tiny_test_config(llm_layers=2)
+    model = build(cfg, seed=12)
+    g = torch.Generator().manual_seed(13)
+    S = cfg.vision_tower_cfg.image_size
+    image = torch.randn(3, S, S, generator=g).to(torch.bfloat16)
+    ids = torch.tensor([[5, cfg.image_token_id, 6, 7, 8, 9, 10],
+                        [11, 12, 13, cfg.pad_token_id, cfg.pad_token_id, cfg.pad_token_id, cfg.pad_token_id],
+                        [14, 15, 16, 17, 18, cfg.pad_token_id, cfg.pad_token_id]])
+    mask = torch.tensor([[1] * 7, [1, 1, 1, 0, 0, 0, 0], [1, 1, 1, 1, 1, 0, 0]], dtype=torch.bool)
+    labels = torch.randint(3, 900, ids.shape, generator=g)
+    plain = model(input_ids=ids, media={"image": [image.cuda()]}, attention_mask=mask, labels=labels)
+    packed = model(input_ids=ids, media={"image": [image.cuda()]}, attention_mask=mask, labels=labels,
+                   force_packing=True)
+    lens = [7 - 1 + 17, 3, 5]
+    assert packed.logits.shape[:2] == (1, sum(lens) + 1)
+    sd = model.state_dict()
+    o32 = oracle_from_state_dict(sd, cfg, torch.float32)
+    off = 0
+    for k, n in enumerate(lens):
+        a = packed.logits[0, off:off + n].float()
+        b = plain.logits[k, :n].float()
+        assert (a - b).abs().max().item() <= 2 ** -6 * max(1.0, b.abs().max().item()), k
+        if k > 0:  # text-only rows: the oracle forward of that sequence alone
+            emb = o32.llm["model.embed_tokens.weight"][ids[k, :n]]
+            from oracle import vila_oracle as O
+            truth, _ = O.qwen2_forward(emb, o32.llm, o32.lcfg)
+            check_close(f"packed row {k} vs oracle", a, truth)
+        off += n
+    assert packed.loss is not None and torch.isfinite(packed.loss)
+    # dpo_forward returns (logits, repacked labels) with the first label of every sequence masked
+    lg, lab = model(input_ids=ids, media={"image": [image.cuda()]}, attention_mask=mask, labels=labels,
+                    force_packing=True, dpo_forward=True)
+    assert lab.shape == (1, sum(lens) + 1) and int(lab[0, 0]) == -100 and int(lab[0, lens[0]]) == -100
+
+
+def test_remote_code_class_stream_and_cli(cuda, tmp_path, capsys):
+    """f1 / f3 / config #1 plumbing on the GPU path: VILAForCausalLM.generate prepends the prompt ids;
+    generate_content(stream=True) yields the same text in chunks; `llava.cli.infer` runs end to end on
+    a checkpoint directory in the reference's three-folder layout."""
+    import numpy as np
+    from PIL import Image as PILImage
+    from vila_b200.model import VILAForCausalLM, tiny_test_config
+    from vila_b200.model.loading import save_pretrained
+    cfg = tiny_test_config(projector="mlp_downsample_3x3_fix", image_aspect_ratio="dynamic", model_max_length=64)
+    model = VILAForCausalLM(cfg, device="cuda").init_random(14)
+    ids, images = synth_inputs(cfg, n_images=1, n_text=8)
+    full = model.generate(input_ids=ids, media={"image": [images[0].cuda()]}, max_new_tokens=6, eos_token_id=None)
+    only = model.generate(input_ids=ids, media={"image": [images[0].cuda()]}, max_new_tokens=6, eos_token_id=None,
+                          return_output_ids_only=True)
+    assert full.shape == (1, ids.shape[1] + 6) and torch.equal(full[:, :ids.shape[1]].cpu(), ids)
+    assert torch.equal(full[:, ids.shape[1]:], only)
+    from types import SimpleNamespace
+    gc = SimpleNamespace(max_new_tokens=12, do_sample=False, eos_token_id=None, pad_token_id=0, max_length=None)
+    img = PILImage.fromarray(np.random.RandomState(3).randint(0, 256, (336, 336, 3), dtype=np.uint8))
+    p_ids, p_media, p_cfg = model._prepare_content([img, "Describe."])
+    new_ids = model.generate(input_ids=p_ids, media=p_media, media_config=p_cfg, generation_config=gc,
+                             return_output_ids_only=True)
+    text = model.tokenizer.decode(new_ids[0], skip_special_tokens=True)
+    chunks = list(model.generate_content([img, "Describe."], generation_config=gc, stream=True))
+    assert len(chunks) >= 2 and " ".join(chunks).split() == text.split()
+    whole = model.generate_content([img, "Describe."], generation_config=gc)   # remote-code: prompt + answer
+    assert whole.split()[-len(text.split()):] == text.split()
+    # a logits processor (the xgrammar hook's interface) steers the eager path
+    class Force:
+        def __call__(self, input_ids, scores):
+            scores = torch.full_like(scores, float("-inf"))
+            scores[..., 42] = 0
+            return scores
+    forced = model.llm.generate(inputs_embeds=model._embed(ids, {"image": [images[0].cuda()]}, {"image": {}}, None, None)[0],
+                                max_new_tokens=4, eos_token_id=None, logits_processor=[Force()])
+    assert forced.tolist() == [[42, 42, 42, 42]]
+    # CLI on a saved checkpoint
+    save_pretrained(model, str(tmp_path / "NVILA-Lite-tiny"))
+    p = tmp_path / "img.png"
+    img.save(p)
+    import llava.cli.infer as infer
+    out = infer.main(["--model-path", str(tmp_path / "NVILA-Lite-tiny"), "--media", str(p), "--text", "Describe."])
+    assert isinstance(out, str) and out in capsys.readouterr().out

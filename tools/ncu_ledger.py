@@ -1,0 +1,212 @@
+"""One launch of every hot-path kernel at its NVILA-8B shape, bracketed by cudaProfilerStart/Stop, for
+
+    ncu --set full --clock-control none --import-source on --profile-from-start off \
+        -k regex:vb:: -f -o gpurun_out/ledger python tools/ncu_ledger.py
+
+Each entry prints `LEDGER <index> <label> <algorithmic bytes> <algorithmic flops>` in launch order so
+tools/ncu_ledger_extract.py can put the algorithmic work beside ncu's dram bytes / durations.
+Without ncu the script simply times every launch with CUDA events (cold L2: a 256 MB scratch write
+between launches), which is the sanity run.
+"""
+import json
+import math
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from vila_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda")
+ops.ensure_workspace(dev)
+g = torch.Generator(device="cuda").manual_seed(0)
+bf = torch.bfloat16
+
+
+def rn(*shape, s=1.0):
+    return (torch.randn(*shape, device=dev, generator=g) * s).to(bf)
+
+
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+ENTRIES = []
+
+
+def entry(label, nbytes, flops, fn, warm=True):
+    ENTRIES.append((label, nbytes, flops, fn, warm))
+
+
+# ---------------- shapes ----------------
+C, Iv, Hv, Dv = 1152, 4304, 16, 72
+Hd, I, Hq, Hkv, D, V = 3584, 18944, 28, 4, 128, 152064
+S = 279
+
+# vision, one 448^2 tile
+px = rn(1, 3, 448, 448)
+entry("im2col_patch14 1x3x448x448", 2 * (3 * 448 * 448 + 1024 * 592), 0, lambda: ops.patch_im2col(px, 14, 592))
+a_pe, w_pe, b_pe, pos = rn(1024, 592), rn(C, 592, s=0.04), rn(C), rn(1024, C)
+entry("gemm patch-embed M=1024 N=1152 K=592 (+bias +pos-emb)", 2 * (1024 * 592 + C * 592 + 2 * 1024 * C),
+      2 * 1024 * C * 588, lambda: ops.linear(a_pe, w_pe, b_pe, residual=pos, res_row_mod=1024, static_w=True))
+x_v = rn(1024, C)
+lnw, lnb = rn(C), rn(C)
+entry("layernorm 1024x1152", 2 * 2 * 1024 * C, 0, lambda: ops.layernorm(x_v, lnw, lnb, 1e-6))
+w_qkv, b_qkv = rn(3 * C, C, s=0.03), rn(3 * C)
+entry("gemm ViT qkv M=1024 N=3456 K=1152", 2 * (1024 * C + 3 * C * C + 1024 * 3 * C), 2 * 1024 * 3 * C * C,
+      lambda: ops.linear(x_v, w_qkv, b_qkv, static_w=True))
+qkv_v = rn(1024, 3, Hv, Dv)
+entry("fmha v1 noncausal d=72 B=1 S=1024 H=16", 2 * 4 * 1024 * C, 4 * 1024 * 1024 * Hv * Dv,
+      lambda: ops.fmha(qkv_v[:, 0], qkv_v[:, 1], qkv_v[:, 2], B=1, Sq=1024, Sk=1024, causal=False, scale=Dv ** -0.5))
+w_o, b_o = rn(C, C, s=0.03), rn(C)
+res_v = rn(1024, C)
+entry("gemm ViT out_proj M=1024 N=1152 K=1152 (+res)", 2 * (3 * 1024 * C + C * C), 2 * 1024 * C * C,
+      lambda: ops.linear(x_v, w_o, b_o, residual=res_v, out=torch.empty_like(res_v), static_w=True))
+w_f1, b_f1 = rn(Iv, C, s=0.03), rn(Iv)
+entry("gemm ViT fc1 M=1024 N=4304 K=1152 (+GELU-tanh)", 2 * (1024 * C + Iv * C + 1024 * Iv), 2 * 1024 * Iv * C,
+      lambda: ops.linear(x_v, w_f1, b_f1, act=ops.ACT_GELU_TANH, static_w=True))
+h_f1 = rn(1024, Iv)
+w_f2, b_f2 = rn(C, Iv, s=0.02), rn(C)
+entry("gemm ViT fc2 M=1024 N=1152 K=4304 (+res, split-K pair)", 2 * (1024 * Iv + C * Iv + 2 * 1024 * C), 2 * 1024 * C * Iv,
+      lambda: ops.linear(h_f1, w_f2, b_f2, residual=res_v, out=torch.empty_like(res_v), static_w=True))
+# projector
+feat = rn(1, 1024, C)
+entry("space_to_depth 1x1024x1152 r=2", 2 * 2 * 1024 * C, 0, lambda: ops.space_to_depth(feat, 32, 32, 2))
+x_p = rn(256, 4 * C)
+lnw4, lnb4 = rn(4 * C), rn(4 * C)
+entry("layernorm 256x4608", 2 * 2 * 256 * 4 * C, 0, lambda: ops.layernorm(x_p, lnw4, lnb4, 1e-5))
+w_p1, b_p1 = rn(Hd, 4 * C, s=0.015), rn(Hd)
+entry("gemm projector fc1 M=256 N=3584 K=4608 (+GELU-erf)", 2 * (256 * 4 * C + Hd * 4 * C + 256 * Hd), 2 * 256 * Hd * 4 * C,
+      lambda: ops.linear(x_p, w_p1, b_p1, act=ops.ACT_GELU_ERF, static_w=True))
+x_p2 = rn(256, Hd)
+w_p2, b_p2 = rn(Hd, Hd, s=0.017), rn(Hd)
+entry("gemm projector fc2 M=256 N=3584 K=3584", 2 * (2 * 256 * Hd + Hd * Hd), 2 * 256 * Hd * Hd,
+      lambda: ops.linear(x_p2, w_p2, b_p2, static_w=True))
+# splice
+table = rn(32768, Hd, s=0.02)
+media = rn(257, Hd)
+src = torch.cat([torch.randint(0, 32768, (14,), device=dev), -torch.arange(1, 258, device=dev),
+                 torch.randint(0, 32768, (8,), device=dev)]).to(torch.int32)
+entry("embed_splice 279 rows", 2 * 2 * S * Hd, 0, lambda: ops.embed_splice(table, media, src))
+# LLM prefill S=279
+x_l = rn(S, Hd, s=0.05)
+nw = rn(Hd)
+entry("rmsnorm 279x3584", 2 * 2 * S * Hd, 0, lambda: ops.rmsnorm(x_l.clone(), nw, 1e-6))
+NQ = (Hq + 2 * Hkv) * D
+wq, bq = rn(NQ, Hd, s=0.02), rn(NQ)
+inv = (1.0 / (1e6 ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))).to(dev)
+posn = torch.arange(S, dtype=torch.int32, device=dev)
+n_pages = 8
+k_pool = torch.zeros(n_pages, 128, Hkv, D, dtype=bf, device=dev)
+v_pool = torch.zeros_like(k_pool)
+pt = torch.arange(n_pages, dtype=torch.int32, device=dev)
+rt = ops.rope_table(posn, D, inv)
+entry("rope_table 279", 2 * S * D, 0, lambda: ops.rope_table(posn, D, inv))
+entry("gemm_skinny qkv+RoPE+KV-append M=279 N=4608 K=3584", 2 * (S * Hd + NQ * Hd + S * NQ), 2 * S * NQ * Hd,
+      lambda: ops.linear_qkv_rope(x_l, wq, bq, rt, Hq, Hkv, D, k_pool, v_pool, pt, 0, static_w=True))
+q_l = rn(S, Hq, D)
+k_pool.copy_(rn(n_pages, 128, Hkv, D))
+v_pool.copy_(rn(n_pages, 128, Hkv, D))
+entry("fmha v1 causal GQA d=128 S=279 paged", 2 * (2 * S * Hq * D + 2 * S * Hkv * D), 2 * S * S * Hq * D,
+      lambda: ops.fmha(q_l, k_pool, v_pool, B=1, Sq=S, Sk=S, causal=True, scale=D ** -0.5, page_table=pt))
+a_o = rn(S, Hq * D)
+wo = rn(Hd, Hq * D, s=0.02)
+entry("gemm_skinny o_proj M=279 N=3584 K=3584 (+res)", 2 * (3 * S * Hd + Hd * Hd), 2 * S * Hd * Hd,
+      lambda: ops.linear(a_o, wo, residual=x_l, out=torch.empty_like(x_l), static_w=True))
+wgu = rn(2 * I, Hd, s=0.02)
+entry("gemm_skinny gate/up SwiGLU M=279 N=37888 K=3584", 2 * (S * Hd + 2 * I * Hd + S * I), 2 * S * 2 * I * Hd,
+      lambda: ops.linear(x_l, wgu, swiglu=True, static_w=True))
+a_d = rn(S, I, s=0.1)
+wd = rn(Hd, I, s=0.01)
+entry("gemm_skinny down M=279 N=3584 K=18944 (+res)", 2 * (S * I + Hd * I + 2 * S * Hd), 2 * S * Hd * I,
+      lambda: ops.linear(a_d, wd, residual=x_l, out=torch.empty_like(x_l), static_w=True))
+# decode
+x1, xa1, xi1 = rn(Hd), rn(Hq * D), rn(I, s=0.1)
+entry("gemv qkv N=4608 K=3584 (+RMSNorm +bias)", 2 * NQ * Hd, 2 * NQ * Hd,
+      lambda: ops.gemv(x1, wq, bias=bq, norm_w=nw, static_w=True))
+entry("gemv o_proj N=3584 K=3584 (+res)", 2 * Hd * Hd, 2 * Hd * Hd,
+      lambda: ops.gemv(xa1, wo, residual=x1, static_w=True))
+entry("gemv gate/up N=37888 K=3584 (+RMSNorm, SwiGLU)", 2 * 2 * I * Hd, 4 * I * Hd,
+      lambda: ops.gemv(x1, wgu, norm_w=nw, swiglu=True, static_w=True))
+entry("gemv down N=3584 K=18944 (+res)", 2 * Hd * I, 2 * Hd * I,
+      lambda: ops.gemv(xi1, wd, residual=x1, static_w=True))
+wlm = rn(V, Hd, s=0.02)
+key = torch.zeros(1, dtype=torch.int64, device=dev)
+entry("gemv lm_head N=152064 K=3584 (+RMSNorm, argmax)", 2 * V * Hd, 2 * V * Hd,
+      lambda: ops.gemv(x1, wlm, norm_w=nw, argmax_key=key, write_out=False, static_w=True))
+tok = torch.zeros(1, dtype=torch.int32, device=dev)
+hist = torch.zeros(8, dtype=torch.int32, device=dev)
+stp = torch.zeros(1, dtype=torch.int32, device=dev)
+pp = torch.zeros(1, dtype=torch.int32, device=dev)
+xn = torch.zeros(Hd, dtype=bf, device=dev)
+entry("argmax_finalize", 2 * Hd * 2, 0, lambda: (stp.zero_(), ops.argmax_finalize(key, tok, hist, stp, pp, table, xn)))
+qkv1 = rn(NQ)
+out1 = torch.zeros(Hq * D, dtype=bf, device=dev)
+ws = torch.zeros(Hkv * 64 * (Hq // Hkv) * (D + 2), dtype=torch.float32, device=dev)
+cnt = torch.zeros(Hkv, dtype=torch.int32, device=dev)
+for ctx, splits in ((279, 8), (16448, 64), (65814, 64)):
+    npg = (ctx + 1 + 127) // 128 + 1
+    kp = rn(npg, 128, Hkv, D)
+    vp = rn(npg, 128, Hkv, D)
+    ptd = torch.arange(npg, dtype=torch.int32, device=dev)
+    pos1 = torch.tensor([ctx], dtype=torch.int32, device=dev)
+    entry("decode_attn ctx=%d splits=%d" % (ctx, splits), 2 * 2 * (ctx + 1) * Hkv * D, 4 * (ctx + 1) * Hq * D,
+          lambda kp=kp, vp=vp, ptd=ptd, pos1=pos1, splits=splits: ops.decode_attention(
+              qkv1, pos1, kp, vp, ptd, out1, ws, cnt, inv, Hq, Hkv, D, splits, D ** -0.5))
+# long / batched shapes
+Sv = 64 * 257 + 22
+npg = (Sv + 127) // 128
+kpv, vpv = rn(npg, 128, Hkv, D), rn(npg, 128, Hkv, D)
+ptv = torch.arange(npg, dtype=torch.int32, device=dev)
+qv = rn(Sv, Hq, D)
+entry("fmha2 causal GQA d=128 S=16470 paged", 2 * (2 * Sv * Hq * D + 2 * Sv * Hkv * D), 2 * Sv * Sv * Hq * D,
+      lambda: ops.fmha(qv, kpv, vpv, B=1, Sq=Sv, Sk=Sv, causal=True, scale=D ** -0.5, page_table=ptv))
+qkv64 = rn(64 * 1024, 3, Hv, Dv)
+entry("fmha2 noncausal d=72 B=64 S=1024 H=16", 2 * 4 * 64 * 1024 * C, 4 * 64 * 1024 * 1024 * Hv * Dv,
+      lambda: ops.fmha(qkv64[:, 0], qkv64[:, 1], qkv64[:, 2], B=64, Sq=1024, Sk=1024, causal=False, scale=Dv ** -0.5))
+x64 = rn(64 * 1024, C)
+entry("gemm pair ViT qkv M=65536 N=3456 K=1152", 2 * (65536 * C + 3 * C * C + 65536 * 3 * C), 2 * 65536 * 3 * C * C,
+      lambda: ops.linear(x64, w_qkv, b_qkv, static_w=True))
+xv = rn(Sv, Hd, s=0.05)
+entry("gemm pair gate/up SwiGLU M=16470 N=37888 K=3584", 2 * (Sv * Hd + 2 * I * Hd + Sv * I), 2 * Sv * 2 * I * Hd,
+      lambda: ops.linear(xv, wgu, swiglu=True, static_w=True))
+qkv_big = rn(Sv, NQ)
+posv = torch.arange(Sv, dtype=torch.int32, device=dev)
+entry("rope_kv_append S=16470", 2 * (2 * Sv * (Hq + Hkv) * D + 2 * Sv * Hkv * D), 0,
+      lambda: ops.rope_kv_append(qkv_big, posv, Hq, Hkv, D, inv, kpv, vpv, ptv, 0))
+entry("rmsnorm 16470x3584", 2 * 2 * Sv * Hd, 0, lambda: ops.rmsnorm(xv.clone(), nw, 1e-6))
+entry("layernorm 65536x1152", 2 * 2 * 65536 * C, 0, lambda: ops.layernorm(x64, lnw, lnb, 1e-6))
+# dynamic-S2 / TSP data movement
+tiles = rn(35, 1024, C)
+entry("s2_merge 35 tiles -> (5,6) x 3456", 2 * (35 * 1024 * C + 30 * 1024 * 3 * C), 0,
+      lambda: ops.s2_merge(tiles, [1, 2, 5], [1, 2, 6], 5, 6))
+ptiles = rn(30, 256, Hd)
+entry("chessboard_merge 30x256x3584", 2 * 2 * 30 * 256 * Hd, 0, lambda: ops.chessboard_merge(ptiles, 5, 6))
+vfe = rn(64, 16, 16, Hd)
+entry("tsp_pool 64x16x16x3584 (8,1,1)", 2 * (64 + 8) * 256 * Hd, 0, lambda: ops.tsp_pool(vfe, 8, 1, 1))
+
+
+def main():
+    rows = []
+    for i, (label, nbytes, flops, fn, warm) in enumerate(ENTRIES):
+        if warm:
+            fn()  # outside the profiler range: attribute setup, TMA descriptor encode
+        torch.cuda.synchronize()
+        flush.fill_(i & 0xff)  # cold L2
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.profiler.start()
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        us = a.elapsed_time(b) * 1e3
+        print("LEDGER %d | %s | %d | %d | %.2f us" % (i, label, nbytes, flops, us), flush=True)
+        rows.append({"index": i, "label": label, "algorithmic_bytes": nbytes, "algorithmic_flops": flops,
+                     "event_us_cold": round(us, 2)})
+    out = Path("gpurun_out")
+    if out.is_dir():
+        (out / "ledger_labels.json").write_text(json.dumps(rows, indent=1))
+
+
+if __name__ == "__main__":
+    main()

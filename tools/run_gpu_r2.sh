@@ -58,7 +58,7 @@ for st in $STAGES; do
       echo "== launches rc=$? lines=$(wc -l < gpurun_out/launches.csv)" ;;
     ledger)
       timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-          -k regex:vb:: -f -o gpurun_out/ledger python tools/ncu_ledger.py > gpurun_out/ledger.log 2>&1
+          --profile-from-start off -k regex:vb:: -f -o gpurun_out/ledger python tools/ncu_ledger.py > gpurun_out/ledger.log 2>&1
       echo "== ledger rc=$?"; ls -la gpurun_out/ledger.ncu-rep ;;
     *)
       if [ -f "tools/$st" ]; then

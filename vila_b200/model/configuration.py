@@ -64,7 +64,10 @@ class LlavaConfig:
     s2_scales: Tuple[int, ...] = (448, 896, 1344)
     s2_max_split_size: int = 448
     s2_resize_output_to_scale_idx: int = -1
+    min_tiles: int = 1
+    max_tiles: int = 12
     num_video_frames: int = 8
+    video_max_tiles: int = 1
     video_encoder: str = "basic"            # "basic" | "tsp"
     tsp_pool_sizes: Tuple[Tuple[int, int, int], ...] = ((8, 1, 1),)
     model_dtype: str = "torch.bfloat16"

@@ -149,26 +149,31 @@ class TSPVideoEncoder(BasicVideoEncoder):
         self.pool_sizes = [tuple(p) for p in pool_sizes]
         self.sep_tokens = sep_tokens
 
+    def _process_features(self, inputs: torch.Tensor, start_token_embeds: Optional[torch.Tensor],
+                          end_token_embeds: Optional[torch.Tensor],
+                          sep_token_embeds: Optional[torch.Tensor]) -> torch.Tensor:
+        """tsp.py:28-51: for every (t, h, w) pool size, mean-pool the frame features (one tsp_pool
+        kernel instead of three chained view+mean ops), add the per-frame start / end tokens, then
+        the separator."""
+        nt, ns = inputs.shape[:2]
+        nl = int(ns ** 0.5)
+        parts = []
+        for pt, ph, pw in self.pool_sizes:
+            f = ops.tsp_pool(inputs.reshape(nt, nl, nl, -1).contiguous(), pt, ph, pw)
+            f = f.flatten(1, 2)
+            f = BasicVideoEncoder._process_features(self, f, start_token_embeds, end_token_embeds)
+            if sep_token_embeds is not None:
+                f = torch.cat([f, sep_token_embeds], dim=0)
+            parts.append(f)
+        return torch.cat(parts, dim=0)
+
     def forward(self, videos: List[torch.Tensor], config: Dict[str, Any]) -> List[torch.Tensor]:
         num_frames = [v.shape[0] for v in videos]
         features = self.parent._encode_frames(torch.cat(videos, dim=0))
         features = torch.split(features, num_frames)
         s, e = self.embed_tokens(self.start_tokens), self.embed_tokens(self.end_tokens)
         sep = self.embed_tokens(self.sep_tokens)
-        outs = []
-        for inputs in features:
-            nt, ns = inputs.shape[:2]
-            nl = int(ns ** 0.5)
-            parts = []
-            for pt, ph, pw in self.pool_sizes:
-                f = ops.tsp_pool(inputs.reshape(nt, nl, nl, -1).contiguous(), pt, ph, pw)
-                f = f.flatten(1, 2)
-                f = BasicVideoEncoder._process_features(self, f, s, e)
-                if sep is not None:
-                    f = torch.cat([f, sep], dim=0)
-                parts.append(f)
-            outs.append(torch.cat(parts, dim=0))
-        return outs
+        return [self._process_features(f, s, e, sep) for f in features]
 
 
 # =================================================================================================
@@ -319,12 +324,28 @@ class LlavaLlamaModel(nn.Module):
             g.replay()
             return static_out
         feats = tower(images)  # [n_tiles, N, C]
+        merged, new_bs = self._s2_merge_split(feats, block_sizes)
+        x = proj(torch.cat(merged, dim=0))
+        outs = []
+        off = 0
+        for ob in new_bs:
+            n = ob[0] * ob[1]
+            outs.append(ops.chessboard_merge(x[off:off + n].contiguous(), ob[0], ob[1]))
+            off += n
+        if all(o.shape[0] == outs[0].shape[0] for o in outs):
+            return torch.stack(outs, dim=0)
+        return outs
+
+    def _s2_merge_split(self, feats: torch.Tensor, block_sizes):
+        """merge_features_for_dynamic_s2 (:298-364) + split_chessboard (:375-378) per image as ONE
+        kernel: -> (list of [bh*bw, N, n_scales*C] re-split tiles, new block sizes)."""
+        tower = self.get_vision_tower()
         scales = tower.scales
         idx = tower.resize_output_to_scale_idx
         ratios = [s // scales[0] for s in scales]
         merged, new_bs = [], []
         cnt = 0
-        for bs in block_sizes:  # merge_features_for_dynamic_s2 (:298-364) + split_chessboard (:375-378)
+        for bs in block_sizes:
             if bs is None:
                 merged.append(ops.s2_merge(feats[cnt:cnt + 1].contiguous(), [1] * len(scales),
                                            [1] * len(scales), 1, 1, share_tile=True))
@@ -342,16 +363,29 @@ class LlavaLlamaModel(nn.Module):
             new_bs.append(ob)
             cnt += n
         assert cnt == len(feats), f"The number of blocks ({cnt}) does not match length of image_features ({len(feats)})!"
-        x = proj(torch.cat(merged, dim=0))
-        outs = []
-        off = 0
-        for ob in new_bs:
-            n = ob[0] * ob[1]
-            outs.append(ops.chessboard_merge(x[off:off + n].contiguous(), ob[0], ob[1]))
-            off += n
-        if all(o.shape[0] == outs[0].shape[0] for o in outs):
-            return torch.stack(outs, dim=0)
-        return outs
+        return merged, new_bs
+
+    def merge_features_for_dynamic_s2(self, image_features, block_sizes):
+        """llava_arch.py:298-364, same return value: ([1, n_scales*C, H, W] feature map per image,
+        new block sizes).  Built from the fused kernel's re-split tiles with one chessboard merge."""
+        merged, new_bs = self._s2_merge_split(image_features, block_sizes)
+        maps = []
+        for tiles, ob in zip(merged, new_bs):
+            side = int(round(tiles.shape[1] ** 0.5))
+            flat = ops.chessboard_merge(tiles.contiguous(), ob[0], ob[1])
+            maps.append(flat.view(ob[0] * side, ob[1] * side, -1).permute(2, 0, 1)[None])
+        return maps, new_bs
+
+    def repack_multimodal_data(self, inputs_embeds, attention_mask, position_ids, labels):
+        """llava_arch.py:557-800.  Without a sequence-parallel group: sequence packing
+        (model/packing.py).  With one, the reference re-shards the batch over ranks (:561-742); here
+        the sharding happens inside the SP prefill (vila_b200/sp.py: zigzag chunks), so the inputs
+        are returned unchanged."""
+        if self._sp_runner() is not None:
+            return inputs_embeds, attention_mask, position_ids, labels
+        from .packing import repack_multimodal_data
+        return repack_multimodal_data(inputs_embeds, attention_mask, position_ids, labels,
+                                      getattr(self, "pad_to_multiple_of", None), self.config.pad_token_id)
 
     # ---- sequence parallelism (LongVILA; reference: llava/train/sequence_parallel/*, the SP branch of
     # repack_multimodal_data llava_arch.py:561-742, eval_vision_niah.py:83-140) ----
@@ -478,10 +512,20 @@ class LlavaLlamaModel(nn.Module):
         runner = self._sp_runner()
         if runner is not None and past_key_values is None:
             return self._forward_sequence_parallel(runner, inputs_embeds, attention_mask, labels, dpo_forward)
-        if force_packing:
-            raise NotImplementedError("sequence packing is a training-time path (SURVEY §8 a14)")
+        extra = {}
+        if force_packing or (packing and self.training and not dpo_forward):
+            # llava_llama.py:117-132: pack the padded batch into one row; the LLM then runs varlen
+            # (block-diagonal causal) attention from `seqlens_in_batch`
+            from .packing import repack_multimodal_data
+            if seqlens_in_batch is None:
+                seqlens_in_batch = torch.sum(attention_mask, dim=1)
+            inputs_embeds, attention_mask, position_ids, labels = repack_multimodal_data(
+                inputs_embeds, attention_mask, position_ids, labels,
+                getattr(self, "pad_to_multiple_of", None), self.config.pad_token_id)
+            extra["seqlens_in_batch"] = seqlens_in_batch
         outputs = self.llm(inputs_embeds=inputs_embeds, attention_mask=attention_mask,
-                           position_ids=position_ids, past_key_values=past_key_values, labels=labels)
+                           position_ids=position_ids, past_key_values=past_key_values, labels=labels,
+                           **extra)
         if dpo_forward:
             return outputs.logits, labels
         return outputs
@@ -548,25 +592,70 @@ class LlavaLlamaModel(nn.Module):
             gc.eos_token_id = self.tokenizer.stop_token_ids
         return gc
 
-    @torch.inference_mode()
-    def generate_content(self, prompt: Union[str, List], generation_config=None,
-                         response_format=None) -> str:
-        """llava_arch.py:835-948: prompt = str or list of (str | image tensor [3,H,W] | PIL image).
-        Image tensors must already be normalised; PIL images go through `media.process_image`."""
+    def get_xgr_logits_processor(self, response_format) -> List[Any]:
+        """llava_arch.py:802-821: compile `response_format` (type json_object | json_schema) with
+        xgrammar into an HF-style logits processor (needs a HF tokenizer; host-side plumbing that the
+        eager decode loop calls once per token)."""
+        import xgrammar as xgr
+        if getattr(self, "grammar_compiler", None) is None:
+            self.grammar_compiler = xgr.GrammarCompiler(
+                xgr.TokenizerInfo.from_huggingface(self.tokenizer, vocab_size=self.vocab_size))
+        if response_format.type == "json_schema":
+            compiled = self.grammar_compiler.compile_json_schema(response_format.json_schema.schema_, indent=2)
+        else:
+            compiled = self.grammar_compiler.compile_builtin_json_grammar()
+        return [xgr.contrib.hf.LogitsProcessor(compiled)]
+
+    def _prepare_content(self, prompt: Union[str, List]):
+        """prompt -> (input_ids [1,T], media, media_config): the host half of generate_content
+        (llava_arch.py:843-897)."""
         from . import media as media_utils
-        if response_format is not None:
-            raise NotImplementedError("xgrammar-constrained decoding is a serving feature (SURVEY §8f.3)")
         text, images = media_utils.extract_media(prompt, self.config)
         media: Dict[str, List[torch.Tensor]] = {}
         media_config: Dict[str, Dict[str, Any]] = defaultdict(dict)
         if images:
             tensors, block_sizes = media_utils.process_images(images, self.config)
+            if (self.config.image_aspect_ratio == "dynamic" and len(images) == 1
+                    and not isinstance(images[0], torch.Tensor)):
+                text = media_utils.dynamic_prompt(text, len(tensors))
             media["image"] = tensors
             if block_sizes is not None:
                 media_config["image"]["block_sizes"] = block_sizes
         ids = media_utils.tokenize_conversation(text, self.tokenizer)
-        input_ids = torch.tensor([ids], dtype=torch.long)
-        gc = generation_config or self.default_generation_config
-        output_ids = self.generate(input_ids=input_ids, media=media, media_config=media_config,
-                                   generation_config=gc)
-        return self.tokenizer.decode(output_ids[0], skip_special_tokens=True).strip()
+        return torch.tensor([ids], dtype=torch.long), media, media_config
+
+    def generate_content(self, prompt: Union[str, List], generation_config=None,
+                         response_format=None, stream: bool = False):
+        """llava_arch.py:835-948: prompt = str or list of (str | image tensor [3,H,W] | PIL image).
+        Image tensors must already be normalised; PIL images go through `media.process_image`.
+        response_format: xgrammar-constrained decoding (llava_arch.py:846-849).
+        stream=True (serving/server.py:259-264 calls it that way): returns an iterator of text
+        chunks; the greedy decode stays on the device and is drained every few tokens."""
+        if stream:
+            return self._generate_content_stream(prompt, generation_config, response_format)
+        with torch.inference_mode():
+            processors = self.get_xgr_logits_processor(response_format) if response_format else None
+            input_ids, media, media_config = self._prepare_content(prompt)
+            gc = generation_config or self.default_generation_config
+            try:
+                output_ids = self.generate(input_ids=input_ids, media=media, media_config=media_config,
+                                           generation_config=gc, logits_processor=processors)
+            except ValueError:
+                if not getattr(gc, "do_sample", False):
+                    raise
+                gc.do_sample = False  # the reference's fallback: retry greedily (llava_arch.py:932-944)
+                output_ids = self.generate(input_ids=input_ids, media=media, media_config=media_config,
+                                           generation_config=gc, logits_processor=processors)
+            return self.tokenizer.decode(output_ids[0], skip_special_tokens=True).strip()
+
+    def _generate_content_stream(self, prompt, generation_config, response_format, chunk_tokens: int = 8):
+        if response_format is not None:
+            raise NotImplementedError("streaming + constrained decoding: use stream=False")
+        with torch.inference_mode():
+            input_ids, media, media_config = self._prepare_content(prompt)
+            gc = generation_config or self.default_generation_config
+            inputs_embeds, _, _ = self._embed(input_ids, media, media_config, None, None)
+        for ids in self.llm.stream_greedy(inputs_embeds[0], gc, chunk_tokens=chunk_tokens):
+            text = self.tokenizer.decode(ids, skip_special_tokens=True)
+            if text:
+                yield text

@@ -50,6 +50,7 @@ def config_from_dir(model_dir: Path) -> LlavaConfig:
     kw = {}
     for k in ("mm_vision_select_layer", "mm_vision_select_feature", "image_aspect_ratio", "dynamic_s2",
               "s2_max_split_size", "s2_resize_output_to_scale_idx", "num_video_frames", "video_encoder",
+              "min_tiles", "max_tiles", "video_max_tiles",
               "model_max_length", "image_token_id", "video_token_id", "pad_token_id"):
         if k in top and top[k] is not None:
             kw[k] = top[k]
@@ -65,7 +66,7 @@ def config_from_dir(model_dir: Path) -> LlavaConfig:
                        mm_projector_type=proj.get("mm_projector_type", "mlp_downsample"), **kw)
 
 
-def load_pretrained(model_path: str, device="cuda") -> LlavaLlamaModel:
+def load_pretrained(model_path: str, device="cuda", model_cls=None) -> LlavaLlamaModel:
     d = Path(model_path)
     cfg = config_from_dir(d)
     tok = None
@@ -84,7 +85,7 @@ def load_pretrained(model_path: str, device="cuda") -> LlavaLlamaModel:
             cfg.image_token_id, cfg.video_token_id = ids["image"], ids["video"]
         except Exception:
             tok = None
-    model = LlavaLlamaModel(cfg, device=device, tokenizer=tok)
+    model = (model_cls or LlavaLlamaModel)(cfg, device=device, tokenizer=tok)
     gc_file = d / "llm" / "generation_config.json"
     if gc_file.exists():  # HF from_pretrained populates model.generation_config from this file
         from types import SimpleNamespace

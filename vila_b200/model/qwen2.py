@@ -229,13 +229,55 @@ class Qwen2ForCausalLM(nn.Module):
             return ops.gemv(h[0], self.lm_head.weight, static_w=True).view(1, -1)
         return ops.linear(h, self.lm_head.weight, static_w=True)
 
+    def forward_packed(self, inputs_embeds: torch.Tensor, attention_mask: torch.Tensor,
+                       position_ids: torch.Tensor, seqlens_in_batch: torch.Tensor) -> torch.Tensor:
+        """Packed (varlen) forward: inputs_embeds [1, T, H] holds the sequences back to back
+        (model/packing.py), `seqlens_in_batch` their lengths; rows past sum(seqlens) (the reference's
+        dummy token / pad_to_multiple_of rows, mask 0) take no part in attention.  Equivalent of HF
+        Qwen2 + flash_attn_varlen_func(cu_seqlens) under the reference's `_get_unpad_data` patch
+        (llava/model/utils/packing.py:12-36): GEMMs / norms / RoPE once over all T rows, block-diagonal
+        causal attention as one tcgen05 FMHA launch per segment.  Returns logits [1, T, V]."""
+        cfg = self.config
+        Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+        x = inputs_embeds[0].to(self.dtype).contiguous().clone()
+        T = x.shape[0]
+        lens = [int(n) for n in seqlens_in_batch.tolist()]
+        assert sum(lens) <= T, "seqlens_in_batch exceed the packed length"
+        pos = position_ids[0].to(device=self.device, dtype=torch.int32).clamp(min=0).contiguous()
+        for layer in self.model.layers:
+            h = ops.rmsnorm(x, layer.input_layernorm.weight, cfg.rms_norm_eps)
+            qkv = ops.linear(h, layer._qkv_w, layer._qkv_b, static_w=True)
+            ops.rope_kv_append(qkv, pos, Hq, Hkv, D, self.inv_freq)  # RoPE in place, no cache
+            q3 = qkv.view(T, Hq + 2 * Hkv, D)
+            attn = torch.zeros(T, Hq, D, dtype=self.dtype, device=self.device)
+            o = 0
+            for n in lens:
+                if n > 0:
+                    ops.fmha(q3[o:o + n, :Hq], q3[o:o + n, Hq:Hq + Hkv], q3[o:o + n, Hq + Hkv:], B=1,
+                             Sq=n, Sk=n, causal=True, scale=D ** -0.5, out=attn[o:o + n])
+                o += n
+            ops.linear(attn.view(T, Hq * D), layer.self_attn.o_proj.weight, residual=x, out=x, static_w=True)
+            h = ops.rmsnorm(x, layer.post_attention_layernorm.weight, cfg.rms_norm_eps)
+            a = ops.linear(h, layer._gu_w, swiglu=True, static_w=True)
+            ops.linear(a, layer.mlp.down_proj.weight, residual=x, out=x, static_w=True)
+        return self.logits_from_hidden(x)[None]
+
     def forward(self, inputs_embeds: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 position_ids: Optional[torch.Tensor] = None, past_key_values=None, labels=None,
-                use_cache: bool = False, **kw):
+                use_cache: bool = False, seqlens_in_batch: Optional[torch.Tensor] = None, **kw):
         """Qwen2ForCausalLM.forward(inputs_embeds=[B,S,H]) -> namespace(logits=[B,S,V], loss=None).
-        Padded positions (attention_mask False) are removed before the kernels and returned as 0."""
+        Padded positions (attention_mask False) are removed before the kernels and returned as 0.
+        seqlens_in_batch: the row is a PACKED batch (forward_packed)."""
         if inputs_embeds.dim() == 2:
             inputs_embeds = inputs_embeds[None]
+        if seqlens_in_batch is not None:
+            out = self.forward_packed(inputs_embeds, attention_mask, position_ids, seqlens_in_batch)
+            loss = None
+            if labels is not None:
+                shift_logits = out[:, :-1].float().reshape(-1, self.vocab_size)
+                shift_labels = labels[:, 1:].reshape(-1).to(out.device).long()
+                loss = torch.nn.functional.cross_entropy(shift_logits, shift_labels, ignore_index=-100)
+            return SimpleNamespace(logits=out, loss=loss, past_key_values=None)
         B, S, _ = inputs_embeds.shape
         out = torch.zeros(B, S, self.vocab_size, dtype=self.dtype, device=self.device)
         for b in range(B):
@@ -361,6 +403,35 @@ class Qwen2ForCausalLM(nn.Module):
                 if hit:
                     return ids[:hit[0] + 1]
         return dec.tokens(done)
+
+    def stream_greedy(self, emb: torch.Tensor, generation_config=None, chunk_tokens: int = 8,
+                      max_new_tokens: Optional[int] = None):
+        """Greedy decode as a generator of id chunks (serving: `generate_content(stream=True)`): the
+        loop stays on the device (CUDA graph); the host drains the token history every `chunk_tokens`
+        tokens, which is also where EOS is noticed."""
+        gc = generation_config or self.generation_config
+        max_new = max_new_tokens or getattr(gc, "max_new_tokens", None)
+        if max_new is None:
+            max_new = max(1, (getattr(gc, "max_length", None) or 20) - emb.shape[0])
+        eos = getattr(gc, "eos_token_id", None)
+        eos_ids = [] if eos is None else ([eos] if isinstance(eos, int) else list(eos))
+        with torch.inference_mode():
+            S = emb.shape[0]
+            dec = self.decoder(max_new)
+            cache = dec.cache_for(S + max_new)
+            hid = self.prefill_hidden_graphed(emb, cache)
+            dec.start(hid[-1], cache)
+            done = 0
+            while done < max_new:
+                n = min(chunk_tokens, max_new - done)
+                dec.run(n)
+                ids = dec.tokens(done + n)[done:]
+                done += n
+                hit = [i for i, t in enumerate(ids) if t in eos_ids]
+                if hit:
+                    yield ids[:hit[0] + 1]
+                    return
+                yield ids
 
     def _generate_eager(self, emb, max_new, eos_ids, sample, processors, temperature, top_p, top_k):
         """Non-graph path: logits come from the same kernels; the token choice (sampling /
