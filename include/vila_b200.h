@@ -117,6 +117,20 @@ int vila_fmha_cfg(int variant, const vila_fmha_params* p, void* stream);
  * out [B*(H/P)*(W/P), k_pad], column = (c, ky, kx); columns >= C*P*P are zero. */
 int vila_patch_im2col(const void* pixels, void* out, int B, int C, int H, int W, int patch,
                       int k_pad, void* stream);
+/* Image preprocessing on the device.  Replaces, per resize grid of
+ * mm_utils.process_image (llava/mm_utils.py:442-522; dynamic_preprocess :299-338, dynamic_s2_preprocess
+ * :341-405), PIL `image.resize((out_w, out_h))` (bicubic; Pillow Resample.c 8bpc fixed point) + the crop
+ * into tile x tile blocks + SiglipImageProcessor.preprocess (rescale 1/255, normalise (x-mean)/std):
+ *   src      uint8 [H, W, 3] (device)      tmp  uint8 scratch [H, out_w, 3]
+ *   coef_*   int32 [out, ksize] 22-bit filter taps, bounds_* int32 [out, 2] = (first input index, count)
+ *            (host: vila_b200.model.media.bicubic_coeffs == Pillow precompute_coeffs/normalize_coeffs_8bpc)
+ *   out      bf16 [n_tiles, 3, tile, tile]; pixel (Y, X) of the resized image lands in tile
+ *            tile_index0 + (Y / tile) * (out_w / tile) + X / tile.  Bit-identical to the PIL path. */
+int vila_resize_bicubic_tiles(const uint8_t* src, int H, int W, int out_w, int out_h,
+                              const int32_t* coef_x, const int32_t* bounds_x, int ksize_x,
+                              const int32_t* coef_y, const int32_t* bounds_y, int ksize_y, uint8_t* tmp,
+                              void* out_tiles, int tile, int tile_index0, float mean, float stdv,
+                              void* stream);
 /* DownSampleBlock.flat_square / flat_square_2x2 / flat_square_3x3 (base_projector.py:58-123):
  * x [B, h*w, C] -> out [B, ceil(h/r)*ceil(w/r), r*r*C], zero padded. */
 int vila_space_to_depth(const void* x, void* out, int B, int h, int w, int C, int r, void* stream);

@@ -122,6 +122,7 @@ def test_prepare_content_dynamic_tiles_on_host():
     m = object.__new__(LlavaLlamaModel)
     torch.nn.Module.__init__(m)
     m.config, m.tokenizer = cfg, SyntheticTokenizer(cfg)
+    m.preprocess_on_device = False  # the host (PIL) path; the kernel path is compared with it under -m gpu
     img = PILImage.fromarray(np.random.RandomState(1).randint(0, 256, (336, 336, 3), dtype=np.uint8))
     ids, media, media_config = m._prepare_content([img, "What is this?"])
     assert len(media["image"]) == 1 and media["image"][0].shape == (3, 448, 448)   # 1x1 grid: no thumbnail

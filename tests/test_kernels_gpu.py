@@ -581,3 +581,36 @@ def test_decode_attention(cuda, ctx, splits):
     assert torch.equal(k_pool[perm[ctx // 128], ctx % 128], kr.transpose(0, 1)[0])
     assert torch.equal(v_pool[perm[ctx // 128], ctx % 128], vn[0])
     assert int(counters.abs().sum()) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# preprocessing kernel (f2): bit-exact vs PIL bicubic + SiglipImageProcessor arithmetic
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h", [(640, 480), (1600, 800), (97, 131), (3000, 500), (448, 448), (333, 1000)])
+@pytest.mark.parametrize("mode", ["resize", "dynamic", "dynamic_s2", "pad"])
+def test_preprocess_tiles_bit_exact_vs_pil(cuda, w, h, mode):
+    """vila_resize_bicubic_tiles through media.process_image_gpu == PIL resize + crop + x/255 +
+    (x-0.5)/0.5 + .to(bf16) (media.process_image, validated against the reference's mm_utils and
+    SiglipImageProcessor), and == the numpy oracle of Pillow's resampler."""
+    import numpy as np
+    from PIL import Image as PILImage
+    from oracle import pil_resample as R
+    from vila_b200.model import LlavaConfig, media
+    _ops()
+    cfg = LlavaConfig(image_aspect_ratio=mode, dynamic_s2=(mode == "dynamic_s2"))
+    img = PILImage.fromarray(np.random.RandomState(w * 3 + h).randint(0, 256, (h, w, 3), dtype=np.uint8))
+    if mode == "dynamic_s2":
+        want, bs = media.process_image(img, cfg, enable_dynamic_s2=True)
+        got, bs2 = media.process_image_gpu(img, cfg)
+        assert tuple(bs) == tuple(bs2)
+    elif mode == "dynamic":
+        want = media.process_image(img, cfg, enable_dynamic_res=True)
+        got = media.process_image_gpu(img, cfg)
+    else:
+        want = media.process_image(img, cfg)[None]
+        got = media.process_image_gpu(img, cfg)
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    assert torch.equal(got.cpu(), want.to(torch.bfloat16))
+    if mode == "resize":  # and against the oracle of the resampler directly
+        u8 = R.resize_bicubic_u8(np.asarray(img), 448, 448)
+        assert torch.equal(got[0].cpu(), torch.from_numpy(R.siglip_normalise(u8)).to(torch.bfloat16))

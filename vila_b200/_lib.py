@@ -74,6 +74,8 @@ SIGNATURES = {
     "vila_fmha": [C.POINTER(FmhaParams), c_void_p],
     "vila_fmha_cfg": [c_int, C.POINTER(FmhaParams), c_void_p],
     "vila_patch_im2col": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "vila_resize_bicubic_tiles": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                  c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p],
     "vila_space_to_depth": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "vila_s2_merge": [c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(c_int), C.POINTER(c_int),
                       c_int, c_int, c_int, c_void_p],

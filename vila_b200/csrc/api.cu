@@ -135,6 +135,16 @@ int vila_patch_im2col(const void* pixels, void* out, int B, int C, int H, int W,
   return vb::im2col_patch14(cb(pixels), mb(out), B, C, H, W, patch, k_pad, st(stream));
 }
 
+int vila_resize_bicubic_tiles(const uint8_t* src, int H, int W, int out_w, int out_h,
+                              const int32_t* coef_x, const int32_t* bounds_x, int ksize_x,
+                              const int32_t* coef_y, const int32_t* bounds_y, int ksize_y, uint8_t* tmp,
+                              void* out_tiles, int tile, int tile_index0, float mean, float stdv,
+                              void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::resize_bicubic_tiles(src, H, W, out_w, out_h, coef_x, bounds_x, ksize_x, coef_y, bounds_y,
+                                  ksize_y, tmp, mb(out_tiles), tile, tile_index0, mean, stdv, st(stream));
+}
+
 int vila_space_to_depth(const void* x, void* out, int B, int h, int w, int C, int r, void* stream) {
   VB_REQUIRE_DEVICE();
   return vb::space_to_depth(cb(x), mb(out), B, h, w, C, r, st(stream));

@@ -272,6 +272,82 @@ __global__ void rope_table_kernel(const int32_t* __restrict__ pos, int S, int ha
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Image preprocessing: PIL's 8-bit bicubic resampler (Pillow src/libImaging/Resample.c:
+// 22-bit fixed-point separable convolution, uint8 after each pass) + SiglipImageProcessor's rescale
+// (1/255) and normalise ((x - mean) / std) + tiling, i.e. what processor.preprocess does to every tile
+// in mm_utils.process_image (llava/mm_utils.py:476,480,505,518) — bit-identical by construction: the
+// integer filter taps come from the host exactly as precompute_coeffs / normalize_coeffs_8bpc make them.
+// ------------------------------------------------------------------------------------------------
+constexpr int kResampleBits = 32 - 8 - 2;
+
+__device__ __forceinline__ uint8_t clip8(int v) {
+  v >>= kResampleBits;  // arithmetic shift, like Pillow's clip8 lookup
+  return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// src [H][W][3] uint8 -> tmp [H][out_w][3] uint8
+__global__ void resize_h_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ tmp, int H, int W,
+                                int out_w, const int32_t* __restrict__ coef,
+                                const int32_t* __restrict__ bounds, int ksize) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const long total = (long)H * out_w;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int X = static_cast<int>(i % out_w);
+    const int y = static_cast<int>(i / out_w);
+    const int xmin = bounds[2 * X], n = bounds[2 * X + 1];
+    const int32_t* k = coef + (long)X * ksize;
+    const uint8_t* p = src + ((long)y * W + xmin) * 3;
+    int a0 = 1 << (kResampleBits - 1), a1 = a0, a2 = a0;
+    for (int x = 0; x < n; ++x) {
+      const int kk = k[x];
+      a0 += p[3 * x] * kk;
+      a1 += p[3 * x + 1] * kk;
+      a2 += p[3 * x + 2] * kk;
+    }
+    uint8_t* d = tmp + i * 3;
+    d[0] = clip8(a0);
+    d[1] = clip8(a1);
+    d[2] = clip8(a2);
+  }
+}
+
+// tmp [H][out_w][3] uint8 -> tiles [n][3][tile][tile] bf16 of the resized (out_h x out_w) image
+__global__ void resize_v_norm_kernel(const uint8_t* __restrict__ tmp, __nv_bfloat16* __restrict__ out,
+                                     int out_w, int out_h, const int32_t* __restrict__ coef,
+                                     const int32_t* __restrict__ bounds, int ksize, int tile, int tile0,
+                                     float mean, float stdv) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const long total = (long)out_h * out_w;
+  const int per_row = out_w / tile;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int X = static_cast<int>(i % out_w);
+    const int Y = static_cast<int>(i / out_w);
+    const int ymin = bounds[2 * Y], n = bounds[2 * Y + 1];
+    const int32_t* k = coef + (long)Y * ksize;
+    const uint8_t* p = tmp + ((long)ymin * out_w + X) * 3;
+    int a[3] = {1 << (kResampleBits - 1), 1 << (kResampleBits - 1), 1 << (kResampleBits - 1)};
+    for (int y = 0; y < n; ++y) {
+      const int kk = k[y];
+      const uint8_t* q = p + (long)y * out_w * 3;
+      a[0] += q[0] * kk;
+      a[1] += q[1] * kk;
+      a[2] += q[2] * kk;
+    }
+    const int t = tile0 + (Y / tile) * per_row + X / tile;
+    const int ly = Y % tile, lx = X % tile;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      // fp32 like the processor: x / 255 (IEEE division), then (x - mean) / std; bf16 RN like .to(bf16)
+      const float v = __fdiv_rn(static_cast<float>(clip8(a[c])), 255.0f);
+      out[(((long)t * 3 + c) * tile + ly) * tile + lx] = __float2bfloat16(__fdiv_rn(v - mean, stdv));
+    }
+  }
+}
+
 }  // namespace
 
 int rope_table(const int32_t* positions, int S, int D, const float* inv_freq, __nv_bfloat16* table,
@@ -370,6 +446,23 @@ int rope_kv_append(__nv_bfloat16* qkv, const int32_t* positions, int S, int Hq, 
   const long total = (long)S * (Hq + 2 * Hkv) * (D / 2);
   VB_CUDA(launch_pdl(rope_kv_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, qkv, positions, S, Hq, Hkv, D, inv_freq,
                                                           k_pool, v_pool, page_table, cache_pos0));
+  return 0;
+}
+
+
+int resize_bicubic_tiles(const uint8_t* src, int H, int W, int out_w, int out_h, const int32_t* coef_x,
+                         const int32_t* bounds_x, int ksize_x, const int32_t* coef_y,
+                         const int32_t* bounds_y, int ksize_y, uint8_t* tmp, __nv_bfloat16* out_tiles,
+                         int tile, int tile_index0, float mean, float stdv, cudaStream_t stream) {
+  VB_CHECK(H > 0 && W > 0 && out_w > 0 && out_h > 0, "resize_bicubic_tiles: empty image");
+  VB_CHECK(tile > 0 && out_w % tile == 0 && out_h % tile == 0,
+           "resize_bicubic_tiles: output %dx%d is not a grid of %d-pixel tiles", out_w, out_h, tile);
+  VB_CHECK(stdv != 0.f, "resize_bicubic_tiles: std must be non-zero");
+  VB_CUDA(launch_pdl(resize_h_kernel, dim3(grid_for((long)H * out_w, 256)), dim3(256), 0, stream, src, tmp,
+                     H, W, out_w, coef_x, bounds_x, ksize_x));
+  VB_CUDA(launch_pdl(resize_v_norm_kernel, dim3(grid_for((long)out_h * out_w, 256)), dim3(256), 0, stream,
+                     static_cast<const uint8_t*>(tmp), out_tiles, out_w, out_h, coef_y, bounds_y, ksize_y,
+                     tile, tile_index0, mean, stdv));
   return 0;
 }
 

@@ -94,6 +94,13 @@ int chessboard_merge(const __nv_bfloat16* tiles, __nv_bfloat16* out, int bh, int
 int tsp_pool(const __nv_bfloat16* x, __nv_bfloat16* out, int T, int h, int w, int C, int pt, int ph,
              int pw, cudaStream_t stream);
 
+// PIL-exact bicubic resize (+ 1/255 rescale, (x-mean)/std, tiling) of a uint8 HWC image into bf16
+// tiles [n, 3, tile, tile]; integer filter taps (Pillow's 22-bit fixed point) come from the host.
+int resize_bicubic_tiles(const uint8_t* src, int H, int W, int out_w, int out_h, const int32_t* coef_x,
+                         const int32_t* bounds_x, int ksize_x, const int32_t* coef_y,
+                         const int32_t* bounds_y, int ksize_y, uint8_t* tmp, __nv_bfloat16* out_tiles,
+                         int tile, int tile_index0, float mean, float stdv, cudaStream_t stream);
+
 // ---- LLM-side data movement ---------------------------------------------------------------------
 // out[i,:] = src[i] >= 0 ? table[src[i],:] : media[-(src[i]+1),:]
 int embed_splice(const __nv_bfloat16* table, const __nv_bfloat16* media, const int32_t* src,

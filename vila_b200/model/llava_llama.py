@@ -614,7 +614,13 @@ class LlavaLlamaModel(nn.Module):
         media: Dict[str, List[torch.Tensor]] = {}
         media_config: Dict[str, Dict[str, Any]] = defaultdict(dict)
         if images:
-            tensors, block_sizes = media_utils.process_images(images, self.config)
+            if getattr(self, "preprocess_on_device", True) and not any(isinstance(im, torch.Tensor) for im in images) \
+                    and next(self.llm.parameters()).is_cuda:
+                # resize + rescale + normalise + tiling as kernels (vila_resize_bicubic_tiles),
+                # bit-identical to the PIL + SiglipImageProcessor path below
+                tensors, block_sizes = media_utils.process_images_gpu(images, self.config, self.device)
+            else:
+                tensors, block_sizes = media_utils.process_images(images, self.config)
             if (self.config.image_aspect_ratio == "dynamic" and len(images) == 1
                     and not isinstance(images[0], torch.Tensor)):
                 text = media_utils.dynamic_prompt(text, len(tensors))

@@ -232,3 +232,125 @@ def tokenize_conversation(text: str, tokenizer) -> List[int]:
                                                  add_generation_prompt=True, tokenize=False)
         return tokenizer(rendered).input_ids
     return tokenizer(text).input_ids
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU preprocessing: PIL's bicubic resize + rescale + normalise + tiling as kernels.
+# The geometry (which grids, which tiles) stays above; what moves to the device is the per-pixel work.
+# Pillow's 8-bit resampler (src/libImaging/Resample.c) is a separable fixed-point convolution: double
+# precision filter weights, normalised, rounded to 22-bit integers, horizontal pass -> uint8 ->
+# vertical pass -> uint8.  The tables below are computed on the host exactly like precompute_coeffs /
+# normalize_coeffs_8bpc do, the two passes run in vila_resize_bicubic_tiles, so the tiles are
+# bit-identical to PIL + SiglipImageProcessor (tests/test_preprocess_*.py).
+# ------------------------------------------------------------------------------------------------
+PRECISION_BITS = 32 - 8 - 2
+
+
+def _bicubic(x: float) -> float:
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def bicubic_coeffs(in_size: int, out_size: int):
+    """-> (ksize, bounds [out,2] (xmin, count), coeffs [out, ksize] int32) of Pillow's
+    precompute_coeffs + normalize_coeffs_8bpc for the full-image box and the bicubic filter."""
+    import math
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds, coeffs = [], []
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        k = [_bicubic((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for w in k:
+            ww += w
+        if ww != 0.0:
+            k = [w / ww for w in k]
+        row = [int(-0.5 + w * (1 << PRECISION_BITS)) if w < 0 else int(0.5 + w * (1 << PRECISION_BITS)) for w in k]
+        coeffs.append(row + [0] * (ksize - xmax))
+        bounds.append((xmin, xmax))
+    return ksize, torch.tensor(bounds, dtype=torch.int32), torch.tensor(coeffs, dtype=torch.int32)
+
+
+def tiling_plan(width: int, height: int, config: LlavaConfig, max_tiles: Optional[int] = None):
+    """The resize jobs of process_image for one image of (width, height): a list of
+    (out_w, out_h) grids in tile order, plus block_size (dynamic_s2) — the same decisions as
+    dynamic_preprocess / dynamic_s2_preprocess / the plain `resize` path, without touching pixels."""
+    size = config.vision_tower_cfg.image_size
+    ar = config.image_aspect_ratio
+    if ar == "dynamic_s2":
+        scales = sorted(config.s2_scales)
+        jobs = [(size * (s // scales[0]), size * (s // scales[0])) for s in scales[:-1]]
+        min_num = (scales[-1] // scales[0]) ** 2
+        best = find_closest_aspect_ratio(width / height, target_ratios(min_num, max_tiles or config.max_tiles),
+                                         width, height, size)
+        jobs.append((size * best[0], size * best[1]))
+        return jobs, (best[1], best[0])
+    if ar == "dynamic":
+        best = find_closest_aspect_ratio(width / height, target_ratios(config.min_tiles, max_tiles or config.max_tiles),
+                                         width, height, size)
+        jobs = [(size * best[0], size * best[1])]
+        if best[0] * best[1] != 1:
+            jobs.append((size, size))  # thumbnail
+        return jobs, None
+    return [(size, size)], None
+
+
+def process_image_gpu(image, config: LlavaConfig, device="cuda", max_tiles: Optional[int] = None):
+    """process_image on the device: PIL image (or uint8 HWC array / tensor) -> bf16 tiles
+    [n, 3, S, S] (+ block_size for dynamic_s2), bit-identical to the PIL + SiglipImageProcessor path.
+    One H2D copy of the raw uint8 image, two kernels per resize grid.  `pad` keeps its host path
+    (a paste on a mean-coloured canvas) and feeds the padded image to the same kernels."""
+    import numpy as np
+
+    from .. import ops
+    if hasattr(image, "convert"):
+        image = image.convert("RGB")
+        if config.image_aspect_ratio == "pad":
+            image = expand2square(image, tuple(int(x * 255) for x in (SIGLIP_MEAN,) * 3))
+        arr = torch.from_numpy(np.asarray(image).copy())
+    else:
+        arr = torch.as_tensor(image)
+    assert arr.dtype == torch.uint8 and arr.dim() == 3 and arr.shape[2] == 3
+    H, W = int(arr.shape[0]), int(arr.shape[1])
+    src = arr.to(device, non_blocking=True)
+    size = config.vision_tower_cfg.image_size
+    jobs, block_size = tiling_plan(W, H, config, max_tiles)
+    n_tiles = sum((w // size) * (h // size) for w, h in jobs)
+    out = torch.empty((n_tiles, 3, size, size), dtype=torch.bfloat16, device=device)
+    t0 = 0
+    for (ow, oh) in jobs:
+        ops.resize_bicubic_tiles(src, ow, oh, out, size, t0, SIGLIP_MEAN, SIGLIP_STD)
+        t0 += (ow // size) * (oh // size)
+    return (out, block_size) if config.image_aspect_ratio == "dynamic_s2" else out
+
+
+def process_images_gpu(images: list, config: LlavaConfig, device="cuda"):
+    """process_images (generate_content's media processing) with the per-pixel work on the device:
+    -> (list of bf16 [3,S,S] device tensors, block_sizes or None), same results as process_images."""
+    ar = config.image_aspect_ratio
+    if len(images) == 1 and ar in ("dynamic", "dynamic_s2"):
+        if ar == "dynamic":
+            tiles = process_image_gpu(images[0], config, device)
+            return [t for t in tiles], None
+        tiles, bs = process_image_gpu(images[0], config, device)
+        return [t for t in tiles], [bs]
+    plain = LlavaConfig(**{**config.__dict__, "image_aspect_ratio": "pad" if ar == "pad" else "resize"})
+    out = [process_image_gpu(im, plain, device)[0] for im in images]
+    return out, ([None] * len(out) if config.dynamic_s2 else None)

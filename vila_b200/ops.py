@@ -155,6 +155,40 @@ def patch_im2col(pixels: torch.Tensor, patch: int, k_pad: int) -> torch.Tensor:
     return out
 
 
+_COEFF_CACHE = {}
+
+
+def _bicubic_tables(in_size: int, out_size: int, device):
+    key = (in_size, out_size, str(device))
+    ent = _COEFF_CACHE.get(key)
+    if ent is None:
+        from .model.media import bicubic_coeffs
+        ksize, bounds, coeffs = bicubic_coeffs(in_size, out_size)
+        if len(_COEFF_CACHE) > 64:
+            _COEFF_CACHE.clear()
+        ent = (ksize, bounds.to(device), coeffs.to(device))
+        _COEFF_CACHE[key] = ent
+    return ent
+
+
+def resize_bicubic_tiles(src: torch.Tensor, out_w: int, out_h: int, out: torch.Tensor, tile: int,
+                         tile_index0: int, mean: float, std: float) -> torch.Tensor:
+    """src uint8 [H, W, 3] (device) -> PIL-exact bicubic resize to (out_w, out_h), rescale, normalise,
+    cut into tile x tile blocks written to out[tile_index0 ...] (bf16 [n, 3, tile, tile])."""
+    _chk(src, "src", torch.uint8); _chk(out, "out")
+    assert src.dim() == 3 and src.shape[2] == 3 and src.is_contiguous() and out.is_contiguous()
+    H, W = int(src.shape[0]), int(src.shape[1])
+    n = (out_w // tile) * (out_h // tile)
+    assert out.shape[1:] == (3, tile, tile) and tile_index0 + n <= out.shape[0]
+    kx, bx, cx = _bicubic_tables(W, out_w, src.device)
+    ky, by, cy = _bicubic_tables(H, out_h, src.device)
+    tmp = torch.empty((H, out_w, 3), dtype=torch.uint8, device=src.device)
+    check(_lib.load().vila_resize_bicubic_tiles(_p(src), H, W, out_w, out_h, _p(cx), _p(bx), kx, _p(cy),
+                                                _p(by), ky, _p(tmp), _p(out), tile, tile_index0, mean,
+                                                std, _stream()), "vila_resize_bicubic_tiles")
+    return out
+
+
 def space_to_depth(x: torch.Tensor, h: int, w: int, r: int) -> torch.Tensor:
     """x [B, h*w, C] -> [B, ceil(h/r)*ceil(w/r), r*r*C]"""
     _chk(x, "x")
