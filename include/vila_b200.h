@@ -43,7 +43,7 @@ extern "C" {
 #define VILA_FLAG_STATIC_W 2
 
 const char* vila_last_error(void);
-int vila_abi_version(void);
+int vila_abi_version(void); /* 2 */
 /* Register caller-owned, ZERO-INITIALISED device scratch (256-byte aligned) used by vila_linear's
  * stream-K schedule for fp32 partial sums (64 KiB of counters + M*N*4 bytes per call that uses it;
  * calls that do not fit simply use the data-parallel schedule).  The kernels leave it zeroed again.
@@ -206,6 +206,29 @@ typedef struct vila_decode_attn_params {
   float scale;
 } vila_decode_attn_params;
 int vila_decode_attention(const vila_decode_attn_params* p, void* stream);
+
+/* Long-context decode attention (video: 16K-66K cached tokens = 34-135 MB of K/V per layer): RoPE +
+ * KV append for the new token, then the tcgen05 FMHA kernel in split-KV mode (the G query heads of a
+ * KV group are the query rows of its 128-row tile; K/V pages stream through TMA on
+ * Hkv * num_splits CTAs), then a deterministic combine.  split j covers tokens
+ * [j*split_tokens, (j+1)*split_tokens) (multiple of 128; num_splits*split_tokens >= max context).
+ * Replaces the same HF calls as vila_decode_attention (apply_rotary_pos_emb + DynamicCache.update +
+ * flash-attn decode, modeling_qwen2.py:99-160,262-310). */
+typedef struct vila_decode_attn_split_params {
+  void* qkv;
+  const int32_t* position;
+  void* k_pool;
+  void* v_pool;
+  const int32_t* page_table;
+  int64_t kv_num_pages;
+  void* out;
+  float* o_partial; /* >= num_splits*Hq*D floats */
+  float* lse;       /* >= num_splits*Hq floats */
+  const float* inv_freq;
+  int32_t Hq, Hkv, D, num_splits, split_tokens;
+  float scale;
+} vila_decode_attn_split_params;
+int vila_decode_attention_split(const vila_decode_attn_split_params* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * vila_decode_mega — n_tokens greedy decode steps of the whole LLM in ONE persistent launch

@@ -614,3 +614,56 @@ def test_preprocess_tiles_bit_exact_vs_pil(cuda, w, h, mode):
     if mode == "resize":  # and against the oracle of the resampler directly
         u8 = R.resize_bicubic_u8(np.asarray(img), 448, 448)
         assert torch.equal(got[0].cpu(), torch.from_numpy(R.siglip_normalise(u8)).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("ctx,splits,split_tokens", [(130, 2, 128), (3000, 12, 256), (16448, 33, 512),
+                                                     (65814, 37, 1792), (65814, 64, 1152), (1000, 37, 512)])
+def test_decode_attention_split_long_context(cuda, ctx, splits, split_tokens):
+    """vila_decode_attention_split (RoPE + append, tcgen05 FMHA in split-KV mode, combine) vs fp32
+    attention over the whole context; (1000, 37, 512): most splits are empty."""
+    from tests.helpers import report_rel
+    ops = _ops()
+    Hq, Hkv, D = 28, 4, 128
+    assert splits * split_tokens >= ctx + 1
+    g = torch.Generator(device="cuda").manual_seed(ctx + splits)
+    n_blk = (ctx + 127) // 128
+    n_pages = (ctx + 1 + 127) // 128 + 3
+    perm = torch.randperm(n_pages, device=cuda, generator=g).to(torch.int32).contiguous()
+    k_hist = bf(torch.randn(ctx, Hkv, D, device=cuda, generator=g))
+    v_hist = bf(torch.randn(ctx, Hkv, D, device=cuda, generator=g))
+    k_pool = bf(torch.randn(n_pages, 128, Hkv, D, device=cuda, generator=g))  # garbage beyond ctx
+    v_pool = bf(torch.randn(n_pages, 128, Hkv, D, device=cuda, generator=g))
+    kp = torch.zeros(n_blk * 128, Hkv, D, dtype=torch.bfloat16, device=cuda)
+    vp = torch.zeros_like(kp)
+    kp[:ctx], vp[:ctx] = k_hist, v_hist
+    tail_k = k_pool[perm[n_blk - 1].long(), ctx % 128:].clone() if ctx % 128 else None
+    k_pool[perm[:n_blk].long()] = kp.view(n_blk, 128, Hkv, D)
+    v_pool[perm[:n_blk].long()] = vp.view(n_blk, 128, Hkv, D)
+    if tail_k is not None:  # keep garbage (not zeros) after the last cached token of the last page
+        k_pool[perm[n_blk - 1].long(), ctx % 128:] = tail_k
+    qkv0 = bf(torch.randn((Hq + 2 * Hkv) * D, device=cuda, generator=g))
+    pos = torch.tensor([ctx], dtype=torch.int32, device=cuda)
+    inv = O.rope_inv_freq(D, 1e6).to(cuda)
+    out = torch.zeros(Hq * D, dtype=torch.bfloat16, device=cuda)
+    o_partial = torch.zeros(splits * Hq * D, dtype=torch.float32, device=cuda)
+    lse = torch.zeros(splits * Hq, dtype=torch.float32, device=cuda)
+    qkv = qkv0.clone()
+    ops.decode_attention_split(qkv, pos, k_pool, v_pool, perm, out, o_partial, lse, inv, Hq, Hkv, D, splits,
+                               split_tokens, D ** -0.5)
+    q = qkv0[:Hq * D].view(1, Hq, D).transpose(0, 1)
+    kn = qkv0[Hq * D:(Hq + Hkv) * D].view(1, Hkv, D).transpose(0, 1)
+    vn = qkv0[(Hq + Hkv) * D:].view(1, Hkv, D)
+    cos, sin = O.rope_cos_sin(torch.tensor([ctx]), D, 1e6, torch.bfloat16)
+    qr, kr = O.apply_rope(q, kn, cos.to(cuda), sin.to(cuda))
+    k_all = torch.cat([k_hist, kr.transpose(0, 1)], 0)
+    v_all = torch.cat([v_hist, vn], 0)
+    ref = ref_attention(qr.transpose(0, 1)[None], k_all[None], v_all[None], True, D ** -0.5)[0, 0]
+    report_rel(f"decode_attention_split ctx={ctx} splits={splits}", out.view(Hq, D), ref, 1.5e-2)
+    assert torch.equal(k_pool[perm[ctx // 128], ctx % 128], kr.transpose(0, 1)[0])
+    assert torch.equal(v_pool[perm[ctx // 128], ctx % 128], vn[0])
+    # the SIMT split kernel on the same problem agrees (both within bf16 noise of the fp32 reference)
+    out2 = torch.zeros_like(out)
+    ws = torch.zeros(Hkv * 16 * (Hq // Hkv) * (D + 2), dtype=torch.float32, device=cuda)
+    counters = torch.zeros(Hkv, dtype=torch.int32, device=cuda)
+    ops.decode_attention(qkv0.clone(), pos, k_pool, v_pool, perm, out2, ws, counters, inv, Hq, Hkv, D, 16, D ** -0.5)
+    report_rel(f"decode_attention (SIMT) ctx={ctx}", out2.view(Hq, D), ref, 1.5e-2)

@@ -151,6 +151,19 @@ for ctx, splits in ((279, 8), (16448, 64), (65814, 64)):
     entry("decode_attn ctx=%d splits=%d" % (ctx, splits), 2 * 2 * (ctx + 1) * Hkv * D, 4 * (ctx + 1) * Hq * D,
           lambda kp=kp, vp=vp, ptd=ptd, pos1=pos1, splits=splits: ops.decode_attention(
               qkv1, pos1, kp, vp, ptd, out1, ws, cnt, inv, Hq, Hkv, D, splits, D ** -0.5))
+o_part = torch.zeros(64 * Hq * D, dtype=torch.float32, device=dev)
+lse_b = torch.zeros(64 * Hq, dtype=torch.float32, device=dev)
+for ctx, splits, st in ((16448, 33, 512), (65814, 37, 1792)):
+    npg = (ctx + 1 + 127) // 128 + 1
+    kp = rn(npg, 128, Hkv, D)
+    vp = rn(npg, 128, Hkv, D)
+    ptd = torch.arange(npg, dtype=torch.int32, device=dev)
+    pos1 = torch.tensor([ctx], dtype=torch.int32, device=dev)
+    # three launches: rope_kv (tiny), fmha split kernel (the K/V stream), combine (tiny)
+    entry("decode_attn_split[3 launches: rope_kv, fmha split, combine] ctx=%d splits=%d" % (ctx, splits),
+          2 * 2 * (ctx + 1) * Hkv * D, 4 * (ctx + 1) * Hq * D,
+          lambda kp=kp, vp=vp, ptd=ptd, pos1=pos1, splits=splits, st=st: ops.decode_attention_split(
+              qkv1.clone(), pos1, kp, vp, ptd, out1, o_part, lse_b, inv, Hq, Hkv, D, splits, st, D ** -0.5))
 # long / batched shapes
 Sv = 64 * 257 + 22
 npg = (Sv + 127) // 128

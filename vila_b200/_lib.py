@@ -46,6 +46,16 @@ class DecodeAttnParams(C.Structure):
     ]
 
 
+class DecodeAttnSplitParams(C.Structure):
+    _fields_ = [
+        ("qkv", c_void_p), ("position", c_void_p), ("k_pool", c_void_p), ("v_pool", c_void_p),
+        ("page_table", c_void_p), ("kv_num_pages", c_i64), ("out", c_void_p), ("o_partial", c_void_p),
+        ("lse", c_void_p), ("inv_freq", c_void_p),
+        ("Hq", C.c_int32), ("Hkv", C.c_int32), ("D", C.c_int32), ("num_splits", C.c_int32),
+        ("split_tokens", C.c_int32), ("scale", c_float),
+    ]
+
+
 class MegaParams(C.Structure):
     _fields_ = [
         ("layers", c_void_p), ("num_layers", C.c_int32),
@@ -92,6 +102,7 @@ SIGNATURES = {
     "vila_argmax_finalize": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_void_p],
     "vila_decode_attention": [C.POINTER(DecodeAttnParams), c_void_p],
+    "vila_decode_attention_split": [C.POINTER(DecodeAttnSplitParams), c_void_p],
     "vila_decode_mega": [C.POINTER(MegaParams), c_void_p],
 }
 _RESTYPES = {"vila_last_error": C.c_char_p}

@@ -42,7 +42,7 @@ static int require_sm100() {
 extern "C" {
 
 const char* vila_last_error(void) { return vb::last_error(); }
-int vila_abi_version(void) { return 1; }
+int vila_abi_version(void) { return 2; }
 
 int vila_set_workspace(void* ptr, uint64_t bytes) { return vb::set_workspace(ptr, (size_t)bytes); }
 
@@ -256,6 +256,24 @@ int vila_decode_attention(const vila_decode_attn_params* p, void* stream) {
   d.Hq = p->Hq; d.Hkv = p->Hkv; d.D = p->D; d.num_splits = p->num_splits;
   d.scale = p->scale;
   return vb::decode_attention(d, st(stream));
+}
+
+int vila_decode_attention_split(const vila_decode_attn_split_params* p, void* stream) {
+  VB_REQUIRE_DEVICE();
+  vb::DecodeAttnSplitParams d;
+  d.qkv = mb(p->qkv);
+  d.position = p->position;
+  d.k_pool = mb(p->k_pool);
+  d.v_pool = mb(p->v_pool);
+  d.page_table = p->page_table;
+  d.kv_num_pages = p->kv_num_pages;
+  d.out = mb(p->out);
+  d.o_partial = p->o_partial;
+  d.lse = p->lse;
+  d.inv_freq = p->inv_freq;
+  d.Hq = p->Hq; d.Hkv = p->Hkv; d.D = p->D; d.num_splits = p->num_splits; d.split_tokens = p->split_tokens;
+  d.scale = p->scale;
+  return vb::decode_attention_split(d, st(stream));
 }
 
 int vila_decode_mega(const vila_mega_params* p, void* stream) {

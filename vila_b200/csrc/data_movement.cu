@@ -241,7 +241,9 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* _
       base[i + half] = __float2bfloat16(x1);
     }
     if (hh >= Hq && k_pool != nullptr) {
-      const int cpos = cache_pos0 + s;
+      // cache_pos0 < 0: the cache slot is the position id itself (decode: the position lives in
+      // device memory so that one captured graph serves every step)
+      const int cpos = cache_pos0 < 0 ? pos[s] : cache_pos0 + s;
       const int page = page_table[cpos >> 7];
       const int hk = (hh - Hq) % Hkv;
       __nv_bfloat16* pool = (hh < Hq + Hkv) ? k_pool : v_pool;

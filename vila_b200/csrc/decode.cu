@@ -493,6 +493,36 @@ decode_attn_kernel(DecodeAttnParams p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// long-context decode attention: combine of the split-KV partials written by fmha_decode_split
+// (tcgen05 FMHA kernel in split mode).  out[h, :] = sum_s w_s * O_s[h, :], w_s = 2^(lse_s - max) / sum.
+// Splits are summed in index order (deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void decode_combine_kernel(const float* __restrict__ o_partial, const float* __restrict__ lse,
+                                      __nv_bfloat16* __restrict__ out, int Hq, int D, int splits) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int h = blockIdx.x;  // query head (= kv head * G + g, the layout of the partials' [Hkv][G])
+  float mx = -INFINITY;
+  for (int s = 0; s < splits; ++s) mx = fmaxf(mx, lse[(long)s * Hq + h]);
+  float den = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float v = lse[(long)s * Hq + h];
+    den += (v == -INFINITY) ? 0.f : exp2f(v - mx);
+  }
+  const float inv = den > 0.f ? 1.f / den : 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float v = lse[(long)s * Hq + h];
+      const float w = (v == -INFINITY) ? 0.f : exp2f(v - mx);
+      acc += w * o_partial[((long)s * Hq + h) * D + d];
+    }
+    out[(long)h * D + d] = __float2bfloat16(acc * inv);
+  }
+}
+
 }  // namespace
 
 int gemv_bf16(const GemvParams& p, cudaStream_t stream) {
@@ -564,6 +594,53 @@ int decode_attention(const DecodeAttnParams& p, cudaStream_t stream) {
       return 1;
   }
 #undef VB_DA_CASE
+  return 0;
+}
+
+
+// Long-context decode attention in three launches (all PDL, graph-capturable, position on the device):
+//   1. rope_kv_append on the one new token: RoPE(q, k_new) in place, k/v appended at slot = position
+//   2. fmha_decode_split: the tcgen05 FMHA kernel with the G query heads of a KV group as its query
+//      rows and the KV splits as blockIdx.z: K/V pages stream through TMA into the warp-specialised
+//      producer / MMA / softmax pipeline on every SM
+//   3. decode_combine_kernel
+int decode_attention_split(const DecodeAttnSplitParams& p, cudaStream_t stream) {
+  VB_CHECK(p.D == 128, "decode_attention_split: head_dim must be 128 (got %d)", p.D);
+  VB_CHECK(p.Hq % p.Hkv == 0, "decode_attention_split: Hq %% Hkv != 0");
+  VB_CHECK(p.num_splits >= 1 && p.split_tokens > 0 && p.split_tokens % 128 == 0,
+           "decode_attention_split: bad split configuration (%d x %d)", p.num_splits, p.split_tokens);
+  const int G = p.Hq / p.Hkv;
+  int rc = rope_kv_append(p.qkv, p.position, 1, p.Hq, p.Hkv, p.D, p.inv_freq, p.k_pool, p.v_pool,
+                          p.page_table, -1, stream);
+  if (rc) return rc;
+  FmhaParams f;
+  f.q = p.qkv;
+  f.q_tok_stride = p.D;                       // "token" = query head g of the group
+  f.q_head_stride = static_cast<int64_t>(G) * p.D;   // "head" = KV head
+  f.k = p.k_pool;
+  f.v = p.v_pool;
+  f.kv_page_stride = static_cast<int64_t>(128) * p.Hkv * p.D;
+  f.kv_tok_stride = static_cast<int64_t>(p.Hkv) * p.D;
+  f.kv_head_stride = p.D;
+  f.kv_num_pages = p.kv_num_pages;
+  f.page_table = p.page_table;
+  f.page_table_stride = 0;
+  f.o = nullptr;
+  f.o_tok_stride = p.D;
+  f.o_head_stride = static_cast<int64_t>(G) * p.D;
+  f.B = p.num_splits;
+  f.Sq = G;
+  f.Sk = p.split_tokens;
+  f.Hq = p.Hkv;
+  f.Hkv = p.Hkv;
+  f.D = p.D;
+  f.causal = 0;
+  f.scale = p.scale;
+  rc = fmha_decode_split(f, p.position, p.split_tokens, p.o_partial, p.lse, stream);
+  if (rc) return rc;
+  VB_CUDA(launch_pdl(decode_combine_kernel, dim3(p.Hq), dim3(128), 0, stream,
+                     static_cast<const float*>(p.o_partial), static_cast<const float*>(p.lse), p.out,
+                     p.Hq, p.D, p.num_splits));
   return 0;
 }
 

@@ -55,6 +55,14 @@ struct FmhaKernelArgs {
   int page_table_stride;
   int Sq, Sk, Hq, Hkv, D, causal, paged;
   float scale_log2;
+  // split-KV decode mode (fmha_decode_split): blockIdx.z is a KV split of ONE sequence, not a batch
+  // entry.  Split z covers tokens [z*split_tokens, min(Sk_total, (z+1)*split_tokens)); Sk_total is read
+  // from device memory (*sk_dev + 1: the position of the token being decoded), the partial outputs go
+  // to o_partial (fp32, normalised per split) with their log2-sum-exp in lse_out.
+  const int32_t* sk_dev;
+  int split_tokens;
+  float* o_partial;  // [splits][Hq][Sq][D]
+  float* lse_out;    // [splits][Hq][Sq]
 };
 
 template <int DP, int CW>
@@ -91,14 +99,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int hk = h / (a.Hq / a.Hkv);
-  const int off = a.Sk - a.Sq;  // causal diagonal offset
-
-  int kv_end = a.Sk;
-  if (a.causal) {
-    int q_last = min((qt + 1) * BQ, a.Sq) - 1;
-    kv_end = min(a.Sk, q_last + off + 1);
-  }
-  const int nblk = (kv_end + BKV - 1) / BKV;
+  const bool split_mode = a.split_tokens > 0;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -124,6 +125,24 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   griddep_launch_dependents();
   griddep_wait();  // Q/K/V come from the predecessor; O may alias memory it still reads
 
+  // KV extent of this CTA (after the dependency wait: in split mode it comes from device memory)
+  int Sk = a.Sk;
+  int blk0 = 0;              // first KV block (page-table index) of this CTA
+  const int qb = split_mode ? 0 : b;  // batch entry the queries / outputs belong to
+  if (split_mode) {
+    const int total = *a.sk_dev + 1;
+    const int start = b * a.split_tokens;
+    blk0 = start / BKV;
+    Sk = max(0, min(a.split_tokens, total - start));
+  }
+  const int off = Sk - a.Sq;  // causal diagonal offset
+  int kv_end = Sk;
+  if (a.causal) {
+    int q_last = min((qt + 1) * BQ, a.Sq) - 1;
+    kv_end = min(Sk, q_last + off + 1);
+  }
+  const int nblk = (kv_end + BKV - 1) / BKV;
+
   if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0 && nblk > 0) {
@@ -133,14 +152,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_arrive_expect_tx(q_full, C::kTileBytes);
 #pragma unroll
       for (int c = 0; c < C::kChunks; ++c)
-        tma_load_4d(q_s + c * C::kChunkBytes, &tm_q, q_full, c * CW, h, b * a.Sq + qt * BQ, 0);
+        tma_load_4d(q_s + c * C::kChunkBytes, &tm_q, q_full, c * CW, h, qb * a.Sq + qt * BQ, 0);
       for (int j = 0; j < nblk; ++j) {
         const int s = j & 1;
         const uint32_t par = ((j >> 1) & 1) ^ 1;
         int tok, page;
         if (a.paged) {
           tok = 0;
-          page = a.page_table ? a.page_table[b * a.page_table_stride + j] : j;
+          page = a.page_table ? a.page_table[split_mode ? blk0 + j : b * a.page_table_stride + j] : blk0 + j;
         } else {
           tok = b * a.Sk + j * BKV;
           page = 0;
@@ -226,8 +245,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
       const uint32_t s_addr = tmem_base + lane_addr + s * BKV;
       const int kv0 = j * BKV;
-      const bool need_mask = (kv0 + BKV > a.Sk) || (a.causal && (kv0 + BKV - 1 > qt * BQ + off));
-      const int kv_lim = a.causal ? min(a.Sk - 1, q_idx + off) : a.Sk - 1;  // last valid kv index
+      const bool need_mask = (kv0 + BKV > Sk) || (a.causal && (kv0 + BKV - 1 > qt * BQ + off));
+      const int kv_lim = a.causal ? min(Sk - 1, q_idx + off) : Sk - 1;  // last valid kv index
 
       // pass 1: row max
       float mx = -INFINITY;
@@ -318,7 +337,20 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
 
-    if (q_idx < a.Sq) {
+    if (split_mode) {
+      if (q_idx < a.Sq) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        const int64_t r = (static_cast<int64_t>(b) * a.Hq + h) * a.Sq + q_idx;
+        a.lse_out[r] = l > 0.f ? m + log2f(l) : -INFINITY;
+        float4* dst = reinterpret_cast<float4*>(a.o_partial + r * a.D);
+#pragma unroll
+        for (int g = 0; g < DP / 4; ++g) {
+          if (g * 4 < a.D)
+            dst[g] = make_float4(o_acc[g * 4] * inv, o_acc[g * 4 + 1] * inv, o_acc[g * 4 + 2] * inv,
+                                 o_acc[g * 4 + 3] * inv);
+        }
+      }
+    } else if (q_idx < a.Sq) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
       __nv_bfloat16* dst = a.o + static_cast<int64_t>(b * a.Sq + q_idx) * a.o_tok_stride +
                            static_cast<int64_t>(h) * a.o_head_stride;
@@ -344,14 +376,23 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 }
 
+struct SplitArgs {
+  const int32_t* sk_dev;
+  int split_tokens;
+  float* o_partial;
+  float* lse_out;
+};
+
 template <int DP, int CW>
-int launch_fmha(const FmhaParams& p, cudaStream_t stream) {
+int launch_fmha(const FmhaParams& p, cudaStream_t stream, const SplitArgs* split = nullptr) {
   using C = FmhaCfg<DP, CW>;
   CUtensorMap tq, tk, tv;
   {
-    uint64_t dims[4] = {(uint64_t)p.D, (uint64_t)p.Hq, (uint64_t)p.B * p.Sq, 1};
+    // split mode: the queries are ONE set of Sq rows shared by all splits (blockIdx.z)
+    const uint64_t q_rows = (uint64_t)(split ? 1 : p.B) * p.Sq;
+    uint64_t dims[4] = {(uint64_t)p.D, (uint64_t)p.Hq, q_rows, 1};
     uint64_t str[3] = {(uint64_t)p.q_head_stride, (uint64_t)p.q_tok_stride,
-                       (uint64_t)p.q_tok_stride * p.B * p.Sq};
+                       (uint64_t)p.q_tok_stride * q_rows};
     uint32_t box[4] = {CW, 1, BQ, 1};
     if (make_tmap_nd_bf16(&tq, p.q, 4, dims, str, box, C::kSwizzleBytes)) return 1;
   }
@@ -380,6 +421,10 @@ int launch_fmha(const FmhaParams& p, cudaStream_t stream) {
   a.causal = p.causal;
   a.paged = paged ? 1 : 0;
   a.scale_log2 = p.scale * 1.4426950408889634f;
+  a.sk_dev = split ? split->sk_dev : nullptr;
+  a.split_tokens = split ? split->split_tokens : 0;
+  a.o_partial = split ? split->o_partial : nullptr;
+  a.lse_out = split ? split->lse_out : nullptr;
   auto kern = fmha_fwd_kernel<DP, CW>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -394,6 +439,22 @@ int launch_fmha(const FmhaParams& p, cudaStream_t stream) {
 }  // namespace
 
 int fmha_prefill(const FmhaParams& p, cudaStream_t stream) { return fmha_prefill_cfg(0, p, stream); }
+
+// Split-KV attention of ONE long sequence for a handful of query rows (decode: the G query heads of a
+// KV group are the "rows" of the 128-row tile, the KV heads are the "heads"): p.B = number of KV
+// splits of split_tokens tokens each, the sequence length is *n_tok_minus_1 + 1 (device memory, read
+// after the dependency wait, so one captured graph serves every decode position), K/V paged.  Writes
+// normalised fp32 partials [B][Hq][Sq][D] and their log2-sum-exp [B][Hq][Sq]; non-causal.
+int fmha_decode_split(const FmhaParams& p, const int32_t* n_tok_minus_1, int split_tokens,
+                      float* o_partial, float* lse, cudaStream_t stream) {
+  VB_CHECK(p.D == 128, "fmha_decode_split: head dim must be 128");
+  VB_CHECK(p.kv_page_stride != 0 && p.page_table != nullptr, "fmha_decode_split: K/V must be paged");
+  VB_CHECK(split_tokens > 0 && split_tokens % BKV == 0, "fmha_decode_split: split_tokens %% 128 != 0");
+  VB_CHECK(p.Sq >= 1 && p.Sq <= BQ && !p.causal, "fmha_decode_split: 1..128 query rows, non-causal");
+  VB_CHECK(n_tok_minus_1 && o_partial && lse, "fmha_decode_split: null output / length pointer");
+  SplitArgs sa{n_tok_minus_1, split_tokens, o_partial, lse};
+  return launch_fmha<128, 64>(p, stream, &sa);
+}
 
 // variant: 0 = size heuristic, 1 = force the one-tile-per-CTA kernel, 2 = force the two-tile kernel
 // (falls through to v1 only when v2 does not cover the head dim / Sq <= 128).

@@ -67,6 +67,9 @@ struct FmhaParams {
 int fmha_prefill(const FmhaParams& p, cudaStream_t stream);
 int fmha_prefill_cfg(int variant, const FmhaParams& p, cudaStream_t stream);  // 0 auto, 1 one-tile, 2 two-tile
 int fmha_prefill_v2(const FmhaParams& p, cudaStream_t stream);  // -1: shape not handled
+// split-KV mode of the one-tile kernel for decode at long context (see fmha_tcgen05.cu)
+int fmha_decode_split(const FmhaParams& p, const int32_t* n_tok_minus_1, int split_tokens,
+                      float* o_partial, float* lse, cudaStream_t stream);
 
 // ---- norms ---------------------------------------------------------------------------------------
 int layernorm_bf16(const __nv_bfloat16* x, const __nv_bfloat16* w, const __nv_bfloat16* b,
@@ -148,6 +151,21 @@ struct DecodeAttnParams {
   float scale;
 };
 int decode_attention(const DecodeAttnParams& p, cudaStream_t stream);
+struct DecodeAttnSplitParams {
+  __nv_bfloat16* qkv;          // [(Hq+2Hkv)*D] pre-RoPE, current token (q / k rotated in place)
+  const int32_t* position;     // device scalar: position id of the current token == tokens cached so far
+  __nv_bfloat16* k_pool;       // this layer's K pages [P,128,Hkv,D]
+  __nv_bfloat16* v_pool;
+  const int32_t* page_table;
+  int64_t kv_num_pages;
+  __nv_bfloat16* out;          // [Hq*D]
+  float* o_partial;            // [num_splits, Hq, D] fp32
+  float* lse;                  // [num_splits, Hq]
+  const float* inv_freq;
+  int Hq, Hkv, D, num_splits, split_tokens;
+  float scale;
+};
+int decode_attention_split(const DecodeAttnSplitParams& p, cudaStream_t stream);
 
 // ---- persistent decode mega-kernel (decode_mega.cu) -------------------------------------------
 struct MegaLayer {  // device-resident array, one entry per decoder layer

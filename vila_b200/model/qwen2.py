@@ -499,27 +499,36 @@ class GraphDecoder:
         self.ws = torch.zeros(Hkv * self.MAX_SPLITS * (Hq // Hkv) * (D + 2), device=dev,
                               dtype=torch.float32)
         self.counters = torch.zeros(Hkv, device=dev, dtype=torch.int32)
+        # long-context path (vila_decode_attention_split): fp32 split partials + their log-sum-exp
+        self.o_partial = torch.zeros(self.MAX_SPLITS * Hq * D, device=dev, dtype=torch.float32)
+        self.lse = torch.zeros(self.MAX_SPLITS * Hq, device=dev, dtype=torch.float32)
+        self.split_tokens = 0  # > 0: the long-context path is active for the current cache
         self.cache: Optional[PagedKVCache] = None
         self.graphs = {}  # num_splits -> captured CUDA graph of one decode step (for self.cache)
         self.launches_per_step = 5 * cfg.num_hidden_layers + 2
 
     @property
     def graph(self):
-        return self.graphs.get(self.num_splits)
+        return self.graphs.get((self.num_splits, self.split_tokens))
 
-    def pick_splits(self, ctx: int) -> int:
-        """KV splits per KV head for a context of `ctx` tokens.  Short contexts: 8 splits = one
-        thread-block cluster per KV head (DSMEM combine, lowest latency).  Long contexts (video:
-        16K-66K tokens = 34-135 MB of K/V per layer) are a bandwidth problem: spread the stream over
-        every SM (Hkv * splits >= #SMs; combine through the fp32 workspace, last CTA reduces)."""
+    LONG_CTX = 2048
+
+    def pick_splits(self, ctx: int):
+        """-> (num_splits, split_tokens).  Short contexts: 8 splits = one thread-block cluster per KV
+        head of the SIMT kernel (DSMEM combine, lowest latency), split_tokens = 0.  Long contexts
+        (video: 16K-66K tokens = 34-135 MB of K/V per layer) are a bandwidth problem: the tcgen05 FMHA
+        kernel in split-KV mode, one CTA per SM (Hkv * splits <= #SMs), every split a whole number of
+        128-token pages and all splits of (nearly) equal length."""
         if self._fixed_splits:
-            return self._fixed_splits
+            return self._fixed_splits, 0
+        if ctx <= self.LONG_CTX:
+            return 8, 0
         Hkv = self.llm.config.num_key_value_heads
-        if ctx <= 2048:
-            return 8
         sms = torch.cuda.get_device_properties(self.llm.device).multi_processor_count
-        per_head = max(8, min(self.MAX_SPLITS, (2 * sms) // Hkv))   # two CTAs per SM
-        return int(min(per_head, max(8, (ctx + 255) // 256)))
+        pages = (ctx + PAGE - 1) // PAGE
+        per_head = max(1, min(self.MAX_SPLITS, sms // Hkv))
+        pps = (pages + per_head - 1) // per_head          # pages per split
+        return (pages + pps - 1) // pps, pps * PAGE
 
     def cache_for(self, tokens: int, page_order_fn=None, order_key=None) -> PagedKVCache:
         """(Re)use a cache big enough; the graphs bake in the pool / page-table pointers.
@@ -533,7 +542,8 @@ class GraphDecoder:
             self._order_key = order_key
             self.graphs = {}
         self.cache.length = 0
-        self.num_splits = self.pick_splits(tokens)
+        self.num_splits, self.split_tokens = self.pick_splits(self.cache.max_tokens if tokens > self.LONG_CTX
+                                                              else tokens)
         return self.cache
 
     def _step(self):
@@ -542,9 +552,15 @@ class GraphDecoder:
         for li, layer in enumerate(llm.model.layers):
             ops.gemv(self.x, layer._qkv_w, bias=layer._qkv_b, norm_w=layer.input_layernorm.weight,
                      norm_eps=cfg.rms_norm_eps, out=self.qkv, static_w=True)
-            ops.decode_attention(self.qkv, self.position, cache.k(li), cache.v(li), cache.page_table,
-                                 self.attn, self.ws, self.counters, llm.inv_freq, Hq, Hkv, D,
-                                 self.num_splits, D ** -0.5)
+            if self.split_tokens:
+                ops.decode_attention_split(self.qkv, self.position, cache.k(li), cache.v(li),
+                                           cache.page_table, self.attn, self.o_partial, self.lse,
+                                           llm.inv_freq, Hq, Hkv, D, self.num_splits, self.split_tokens,
+                                           D ** -0.5)
+            else:
+                ops.decode_attention(self.qkv, self.position, cache.k(li), cache.v(li), cache.page_table,
+                                     self.attn, self.ws, self.counters, llm.inv_freq, Hq, Hkv, D,
+                                     self.num_splits, D ** -0.5)
             ops.gemv(self.attn, layer.self_attn.o_proj.weight, residual=self.x, out=self.x, static_w=True)
             ops.gemv(self.x, layer._gu_w, norm_w=layer.post_attention_layernorm.weight,
                      norm_eps=cfg.rms_norm_eps, swiglu=True, out=self.act, static_w=True)
@@ -576,13 +592,13 @@ class GraphDecoder:
             self._started = 2
         if n <= 0:
             return
-        g = self.graphs.get(self.num_splits)
+        g = self.graphs.get((self.num_splits, self.split_tokens))
         if g is None:
             # warm-up launch outside capture is not allowed to change state: capture directly
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._step()
-            self.graphs[self.num_splits] = g
+            self.graphs[(self.num_splits, self.split_tokens)] = g
         for _ in range(n):
             g.replay()
         self.cache.length += n

@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import DecodeAttnParams, FmhaParams, GemvParams, check
+from ._lib import DecodeAttnParams, DecodeAttnSplitParams, FmhaParams, GemvParams, check
 
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SILU = 0, 1, 2, 3
 
@@ -340,3 +340,18 @@ def decode_attention(qkv: torch.Tensor, position: torch.Tensor, k_pool: torch.Te
     p.inv_freq = _p(inv_freq)
     p.Hq, p.Hkv, p.D, p.num_splits, p.scale = Hq, Hkv, D, num_splits, scale
     check(_lib.load().vila_decode_attention(C.byref(p), _stream()), "vila_decode_attention")
+
+
+def decode_attention_split(qkv: torch.Tensor, position: torch.Tensor, k_pool: torch.Tensor,
+                           v_pool: torch.Tensor, page_table: torch.Tensor, out: torch.Tensor,
+                           o_partial: torch.Tensor, lse: torch.Tensor, inv_freq: torch.Tensor, Hq: int,
+                           Hkv: int, D: int, num_splits: int, split_tokens: int, scale: float) -> None:
+    """Long-context decode attention: RoPE + KV append, tcgen05 FMHA in split-KV mode, combine."""
+    assert o_partial.dtype == torch.float32 and o_partial.numel() >= num_splits * Hq * D
+    assert lse.dtype == torch.float32 and lse.numel() >= num_splits * Hq
+    p = DecodeAttnSplitParams()
+    p.qkv, p.position, p.k_pool, p.v_pool = _p(qkv), _p(position), _p(k_pool), _p(v_pool)
+    p.page_table, p.kv_num_pages, p.out = _p(page_table), k_pool.shape[0], _p(out)
+    p.o_partial, p.lse, p.inv_freq = _p(o_partial), _p(lse), _p(inv_freq)
+    p.Hq, p.Hkv, p.D, p.num_splits, p.split_tokens, p.scale = Hq, Hkv, D, num_splits, split_tokens, scale
+    check(_lib.load().vila_decode_attention_split(C.byref(p), _stream()), "vila_decode_attention_split")
