@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     # and every ctypes signature corresponds to a declared function
     for n in _lib.SIGNATURES:
         assert n in names, f"{n} bound in _lib.py but not declared in the header"
-    assert lib.vila_abi_version() == 1
+    assert lib.vila_abi_version() == 2
 
 
 def test_struct_layouts_match_header_field_order():
