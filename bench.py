@@ -417,7 +417,13 @@ def run_ours(args):
     clock_summary = clocks.summary()
     peaks = read_peaks()
     ledger = decode_kernel_ledger(model, peaks, ctx=S)
-    video = None if (args.profile or args.no_video) else video_decode_block(model, peaks)
+    video = None
+    if not (args.profile or args.no_video):
+        try:
+            video = video_decode_block(model, peaks)
+        except Exception as e:  # the headline line must survive a failure of an extra block
+            video = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            torch.cuda.synchronize()
 
     step_ms = [a + b for a, b in zip(ttfts, decs)]
     local_stats = torch.tensor([sum(step_ms) / len(step_ms), sum(decs) / len(decs), sum(ttfts) / len(ttfts),

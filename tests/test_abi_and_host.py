@@ -34,6 +34,7 @@ def test_struct_layouts_match_header_field_order():
     text = (ROOT / "include" / "vila_b200.h").read_text()
     for cname, cls in (("vila_fmha_params", _lib.FmhaParams), ("vila_gemv_params", _lib.GemvParams),
                        ("vila_decode_attn_params", _lib.DecodeAttnParams),
+                       ("vila_decode_attn_split_params", _lib.DecodeAttnSplitParams),
                        ("vila_mega_params", _lib.MegaParams)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)

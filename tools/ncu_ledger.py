@@ -201,14 +201,20 @@ def main():
     rows = []
     for i, (label, nbytes, flops, fn, warm) in enumerate(ENTRIES):
         if warm:
-            fn()  # outside the profiler range: attribute setup, TMA descriptor encode
+            try:
+                fn()  # outside the profiler range: attribute setup, TMA descriptor encode
+            except Exception:
+                pass
         torch.cuda.synchronize()
         flush.fill_(i & 0xff)  # cold L2
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.profiler.start()
         a.record()
-        fn()
+        try:
+            fn()
+        except Exception as e:
+            print("LEDGER %d | %s | FAILED %s" % (i, label, str(e)[:200]), flush=True)
         b.record()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
