@@ -15,7 +15,9 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *   - every function returns 0 on success; non-zero on error, message via vila_last_error()
  *     (thread-local). Nothing falls back to the CPU: without an sm_100a device calls fail.
- *   - no hidden global state: KV pool, page tables, workspaces and counters are caller-allocated.
+ *   - no hidden state beyond (a) the per-device stream-K scratch registered with vila_set_workspace and
+ *     (b) per-device "function attributes set" flags: KV pool, page tables, workspaces and counters
+ *     are caller-allocated.
  */
 #ifndef VILA_B200_H_
 #define VILA_B200_H_
@@ -47,7 +49,8 @@ int vila_abi_version(void); /* 2 */
 /* Register caller-owned, ZERO-INITIALISED device scratch (256-byte aligned) used by vila_linear's
  * stream-K schedule for fp32 partial sums (64 KiB of counters + M*N*4 bytes per call that uses it;
  * calls that do not fit simply use the data-parallel schedule).  The kernels leave it zeroed again.
- * One workspace serves one stream at a time.  ptr == NULL unregisters. */
+ * The registration is per DEVICE (the current device at the time of the call); one workspace serves
+ * one stream at a time.  ptr == NULL unregisters. */
 int vila_set_workspace(void* ptr, uint64_t bytes);
 /* fills SM count and compute capability of the current device */
 int vila_device_info(int* sm_count, int* cc_major, int* cc_minor);

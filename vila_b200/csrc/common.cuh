@@ -442,4 +442,17 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 const char* last_error();
 
+// One-time per-DEVICE setup guard (cudaFuncSetAttribute is per device; a process may drive several).
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 0 || d >= 64) d = 0;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 }  // namespace vb

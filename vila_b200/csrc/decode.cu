@@ -543,10 +543,9 @@ int gemv_bf16(const GemvParams& p, cudaStream_t stream) {
   VB_CHECK(smem <= 200 * 1024, "gemv: K=%d / rows_per_block=%d exceed shared memory", p.K,
            rows_per_block);
   auto kern = gemv_kernel<8>;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   VB_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemvThreads), smem, stream, p, rows_per_block, ksplit));
   return 0;
@@ -574,10 +573,9 @@ int decode_attention(const DecodeAttnParams& p, cudaStream_t stream) {
     const bool use_cluster = p.num_splits <= 8;                                                 \
     auto kern = use_cluster ? decode_attn_kernel<128, GG, true> : decode_attn_kernel<128, GG, false>; \
     const size_t smem = (size_t)kDaWarps * 2 * GG * (128 + 2) * sizeof(float);                  \
-    static bool attr_done[2] = {false, false};                                                  \
-    if (!attr_done[use_cluster]) {                                                              \
+    static PerDeviceOnce attr_once[2];                                                          \
+    if (attr_once[use_cluster].first()) {                                                       \
       VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_done[use_cluster] = true;                                                            \
     }                                                                                           \
     VB_CUDA(launch_pdl_cluster(kern, grid, dim3(kDaThreads), smem, stream,                      \
                                dim3(1, use_cluster ? p.num_splits : 1, 1), p));                 \

@@ -604,10 +604,9 @@ int decode_mega(const MegaParams& pin, cudaStream_t stream) {
 #define VB_MEGA_CASE(GG)                                                                         \
   case GG: {                                                                                     \
     auto kern = decode_mega_kernel<GG>;                                                          \
-    static bool attr_done = false;                                                               \
-    if (!attr_done) {                                                                            \
+    static PerDeviceOnce attr_once;                                                              \
+    if (attr_once.first()) {                                                                     \
       VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); \
-      attr_done = true;                                                                          \
     }                                                                                            \
     int occ = 0;                                                                                 \
     VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MT, smem));                \

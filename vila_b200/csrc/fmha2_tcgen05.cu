@@ -404,10 +404,9 @@ int launch_fmha2(const FmhaParams& p, cudaStream_t stream) {
   a.paged = paged ? 1 : 0;
   a.scale_log2 = p.scale * 1.4426950408889634f;
   auto kern = fmha2_fwd_kernel<DP, CW>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    attr_set = true;
   }
   const int q_tiles = (p.Sq + BQ - 1) / BQ;
   dim3 grid((q_tiles + 1) / 2, p.Hq, p.B);

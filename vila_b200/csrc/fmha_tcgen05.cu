@@ -426,10 +426,9 @@ int launch_fmha(const FmhaParams& p, cudaStream_t stream, const SplitArgs* split
   a.o_partial = split ? split->o_partial : nullptr;
   a.lse_out = split ? split->lse_out : nullptr;
   auto kern = fmha_fwd_kernel<DP, CW>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    attr_set = true;
   }
   dim3 grid((p.Sq + BQ - 1) / BQ, p.Hq, p.B);
   VB_CUDA(launch_pdl(kern, grid, dim3(kThreads), C::kSmem, stream, tq, tk, tv, a));

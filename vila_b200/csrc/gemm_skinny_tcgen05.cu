@@ -528,10 +528,9 @@ int launch_skinny(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int l
   if (stages < 2) return -1;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + kStgBytes + 256 + 1024;
   auto kern = gemm_skinny_kernel<kPair>;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
   }
   // cluster split-K (single-CTA flavour): largest split count whose clusters are all co-resident
   int cluster_k = 0;

@@ -511,7 +511,14 @@ struct Workspace {
   void* ptr = nullptr;
   size_t bytes = 0;
 };
-Workspace g_ws;
+// one registration per DEVICE (a process may drive several GPUs; the scratch is device memory)
+Workspace g_ws_dev[64];
+inline Workspace& cur_ws() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return g_ws_dev[(d < 0 || d >= 64) ? 0 : d];
+}
+#define g_ws cur_ws()
 constexpr size_t kCounterBytes = 64 * 1024;  // 16384 tile counters
 
 template <int BLOCK_N, int kStages, int kMode = kModeSingle>
@@ -525,10 +532,9 @@ int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw
   if (make_tmap_2d_bf16(&ta, A, M, K, lda, BLOCK_M, BLOCK_K, 128)) return 1;
   if (make_tmap_2d_bf16(&tw, W, N, K, ldw, S::kBRows, BLOCK_K, 128)) return 1;
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, kStages, kMode>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
   }
   const int sms = num_sms();
   const int tiles = ((M + TILE_M - 1) / TILE_M) * ((N + BLOCK_N - 1) / BLOCK_N);

@@ -272,11 +272,10 @@ int gemv_tma_bf16(const GemvParams& p, cudaStream_t stream) {
   }
   L.bar_off = (L.ring_off + kWarps * L.stages * chunk_bytes + 127) / 128 * 128;
   L.total = L.bar_off + kWarps * kMaxStages * 8;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     VB_CUDA(cudaFuncSetAttribute(gemv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  224 * 1024));
-    attr = true;
   }
   VB_CUDA(launch_pdl(gemv_tma_kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(L.total), stream,
                      p, rows_per_block, ksplit, L));

@@ -137,11 +137,10 @@ int layernorm_bf16(const __nv_bfloat16* x, const __nv_bfloat16* w, const __nv_bf
   VB_CHECK(cols * 2 <= 96 * 1024, "layernorm: row too long (%d)", cols);
   if (rows == 0) return 0;
   const size_t smem = static_cast<size_t>(cols) * 2;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     VB_CUDA(cudaFuncSetAttribute(layernorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  96 * 1024));
-    attr = true;
   }
   VB_CUDA(launch_pdl(layernorm_kernel, dim3(rows), dim3(kNormThreads), smem, stream, x, w, b, out, cols, eps));
   return 0;
@@ -154,11 +153,10 @@ int rmsnorm_bf16(__nv_bfloat16* x_inout, const __nv_bfloat16* residual_add,
   VB_CHECK(cols * 2 <= 96 * 1024, "rmsnorm: row too long (%d)", cols);
   if (rows == 0) return 0;
   const size_t smem = static_cast<size_t>(cols) * 2;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     VB_CUDA(cudaFuncSetAttribute(rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  96 * 1024));
-    attr = true;
   }
   VB_CUDA(launch_pdl(rmsnorm_kernel, dim3(rows), dim3(kNormThreads), smem, stream, x_inout, residual_add, w,
                      out, cols, eps));
