@@ -55,7 +55,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 struct TmaGemvLayout {
   int chunk_elems;   // K / ksplit
   int stages;
-  int x_off, acc_off, ring_off, bar_off, total;
+  int x_off, nw_off, acc_off, ring_off, bar_off, total;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -80,8 +80,13 @@ gemv_tma_kernel(GemvParams p, int rows_per_block, int ksplit, TmaGemvLayout L) {
   uint8_t* my_ring = ring + static_cast<size_t>(warp) * L.stages * chunk_bytes;
   uint64_t* my_bars = bars + warp * kMaxStages;
 
+  uint64_t* x_bar = bars + kWarps * kMaxStages;  // [0]: x arrived, [1]: norm weight arrived
   if (lane == 0) {
     for (int s = 0; s < L.stages; ++s) mbar_init(&my_bars[s], 1);
+    if (warp == 0) {
+      mbar_init(&x_bar[0], 1);
+      mbar_init(&x_bar[1], 1);
+    }
     fence_barrier_init();
   }
   __syncwarp();
@@ -97,22 +102,39 @@ gemv_tma_kernel(GemvParams p, int rows_per_block, int ksplit, TmaGemvLayout L) {
   };
 
   const bool early = (p.flags & 2) != 0;  // static weights: stream before the dependency wait
+  const uint32_t x_bytes = static_cast<uint32_t>(p.K) * 2;
+  uint4* nws = reinterpret_cast<uint4*>(smem + L.nw_off);
   int issued = 0;
   if (early && lane == 0) {
     for (; issued < L.stages && issued < n_my; ++issued) issue(issued);
+    if (warp == 0 && p.norm_w != nullptr) {  // the norm weight is a parameter as well
+      mbar_arrive_expect_tx(&x_bar[1], x_bytes);
+      bulk_g2s(nws, p.norm_w, x_bytes, &x_bar[1]);
+    }
   }
   griddep_wait();
-  if (!early && lane == 0) {
-    for (; issued < L.stages && issued < n_my; ++issued) issue(issued);
+  // ---- prologue: x arrives as ONE bulk copy (a register-staged loop of dependent LDG -> STS round
+  // trips cost ~0.6 us per 4 KB slice: 6 us for the down projection's 38 KB activation vector, during
+  // which the full weight rings stalled the HBM stream) ----
+  if (lane == 0) {
+    if (warp == 0) {
+      mbar_arrive_expect_tx(&x_bar[0], x_bytes);
+      bulk_g2s(xs, p.x, x_bytes, &x_bar[0]);
+      if (!early && p.norm_w != nullptr) {
+        mbar_arrive_expect_tx(&x_bar[1], x_bytes);
+        bulk_g2s(nws, p.norm_w, x_bytes, &x_bar[1]);
+      }
+    }
+    if (!early)
+      for (; issued < L.stages && issued < n_my; ++issued) issue(issued);
   }
-
-  // ---- prologue: stage x (optionally RMS-normalised) in shared memory ----
-  const uint4* xg = reinterpret_cast<const uint4*>(p.x);
+  if (threadIdx.x == 0) best_s = 0ull;
+  __syncthreads();  // barrier initialisation by warp 0 is visible to every warp
+  mbar_wait(&x_bar[0], 0);
   if (p.norm_w != nullptr) {
     float s = 0.f;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-      const uint4 v = ldg_v4(xg + i);
-      xs[i] = v;
+      const uint4 v = xs[i];
       float t;
       t = bf_lo(v.x); s += t * t;
       t = bf_hi(v.x); s += t * t;
@@ -129,9 +151,9 @@ gemv_tma_kernel(GemvParams p, int rows_per_block, int ksplit, TmaGemvLayout L) {
     float t = lane < kWarps ? red[lane] : 0.f;
     t = warp_sum(t);
     const float rstd = rsqrtf(t / p.K + p.norm_eps);
-    const uint4* wv = reinterpret_cast<const uint4*>(p.norm_w);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-      const uint4 v = xs[i], g = ldg_v4(wv + i);
+    mbar_wait(&x_bar[1], 0);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {  // each thread rewrites only its own slots
+      const uint4 v = xs[i], g = nws[i];
       uint4 o;
       o.x = pack_bf16(bf16_round(bf_lo(v.x) * rstd) * bf_lo(g.x), bf16_round(bf_hi(v.x) * rstd) * bf_hi(g.x));
       o.y = pack_bf16(bf16_round(bf_lo(v.y) * rstd) * bf_lo(g.y), bf16_round(bf_hi(v.y) * rstd) * bf_hi(g.y));
@@ -139,10 +161,7 @@ gemv_tma_kernel(GemvParams p, int rows_per_block, int ksplit, TmaGemvLayout L) {
       o.w = pack_bf16(bf16_round(bf_lo(v.w) * rstd) * bf_lo(g.w), bf16_round(bf_hi(v.w) * rstd) * bf_hi(g.w));
       xs[i] = o;
     }
-  } else {
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) xs[i] = ldg_v4(xg + i);
   }
-  if (threadIdx.x == 0) best_s = 0ull;
   __syncthreads();
 
   // ---- main loop: consume this warp's ring ----
@@ -237,7 +256,11 @@ int gemv_tma_bf16(const GemvParams& p, cudaStream_t stream) {
   // the rings to let the next kernel's CTA co-reside (PDL) dropped the gate/up GEMV from 97 % to
   // 76 % of the measured HBM peak (profiles/r01_gemv_variants.md).
   constexpr int kSmemBudget = 220 * 1024;
-  const int x_bytes = (p.K * 2 + 127) / 128 * 128;
+  // x and the norm weight arrive by bulk copy: 16-byte aligned sources (else: register-staged kernel)
+  if ((reinterpret_cast<uintptr_t>(p.x) & 15) || (p.norm_w && (reinterpret_cast<uintptr_t>(p.norm_w) & 15)))
+    return -1;
+  const int x1_bytes = (p.K * 2 + 127) / 128 * 128;
+  const int x_bytes = x1_bytes * (p.norm_w ? 2 : 1);  // x (+ norm weight staging)
   TmaGemvLayout L;
   int ksplit = -1;
   for (int ks = 1; ks <= 128; ++ks) {
@@ -248,7 +271,7 @@ int gemv_tma_bf16(const GemvParams& p, cudaStream_t stream) {
     if (cb > 8192) continue;
     if (cb < 512) break;
     const int acc_bytes = (rows_per_block * ks * 4 + 127) / 128 * 128;
-    const int ring_budget = kSmemBudget - x_bytes - acc_bytes - kWarps * kMaxStages * 8 - 256;
+    const int ring_budget = kSmemBudget - x_bytes - acc_bytes - (kWarps * kMaxStages + 2) * 8 - 256;
     int st = ring_budget / (kWarps * cb);
     if (st > kMaxStages) st = kMaxStages;
     if (st < 3) continue;  // need a few chunks in flight per warp
@@ -260,18 +283,19 @@ int gemv_tma_bf16(const GemvParams& p, cudaStream_t stream) {
   L.chunk_elems = p.K / ksplit;
   const int chunk_bytes = L.chunk_elems * 2;
   L.x_off = 0;
+  L.nw_off = x1_bytes;
   L.acc_off = x_bytes;
   L.ring_off = (L.acc_off + rows_per_block * ksplit * 4 + 127) / 128 * 128;
   {
     // recompute stages for the final ksplit (the loop may have broken on an earlier candidate)
-    const int ring_budget = kSmemBudget - L.ring_off - kWarps * kMaxStages * 8 - 256;
+    const int ring_budget = kSmemBudget - L.ring_off - (kWarps * kMaxStages + 2) * 8 - 256;
     int st = ring_budget / (kWarps * chunk_bytes);
     if (st > kMaxStages) st = kMaxStages;
     if (st < 2) return -1;
     L.stages = st;
   }
   L.bar_off = (L.ring_off + kWarps * L.stages * chunk_bytes + 127) / 128 * 128;
-  L.total = L.bar_off + kWarps * kMaxStages * 8;
+  L.total = L.bar_off + (kWarps * kMaxStages + 2) * 8;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
     VB_CUDA(cudaFuncSetAttribute(gemv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
