@@ -11,7 +11,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-rep = Path(sys.argv[1] if len(sys.argv) > 1 else ROOT / "gpurun_out/ledger.ncu-rep")
+rep = Path(sys.argv[1] if len(sys.argv) > 1 else ROOT / "gpurun_out/ledger_raw.csv")
 labels = json.loads((rep.parent / "ledger_labels.json").read_text())
 peaks = {"hbm_gbs": 6574.5, "bf16_tflops": 1724.0}
 pk = ROOT / "MEASURED_PEAKS.json"
@@ -19,7 +19,10 @@ if pk.exists():
     d = json.loads(pk.read_text())
     peaks = {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"])}
 
-raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if rep.suffix == ".csv":
+    raw = rep.read_text()
+else:
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}

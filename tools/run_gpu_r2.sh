@@ -57,9 +57,21 @@ for st in $STAGES; do
           --log-file gpurun_out/launches.csv python bench.py --profile --steps 1 > gpurun_out/launches.log 2>&1
       echo "== launches rc=$? lines=$(wc -l < gpurun_out/launches.csv)" ;;
     ledger)
-      timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-          --profile-from-start off -k regex:vb:: -f -o gpurun_out/ledger python tools/ncu_ledger.py > gpurun_out/ledger.log 2>&1
-      echo "== ledger rc=$?"; ls -la gpurun_out/ledger.ncu-rep ;;
+      # ncu --set full of one launch per hot kernel; the raw page is exported on the box (csv, small) and
+      # the report itself kept only if it fits the 64 MiB return budget
+      timeout 1500 ncu --set full --clock-control none --kernel-name-base demangled \
+          --profile-from-start off -k regex:vb:: -f -o /tmp/ledger python tools/ncu_ledger.py > gpurun_out/ledger.log 2>&1
+      echo "== ledger rc=$?"; ls -la /tmp/ledger.ncu-rep
+      ncu -i /tmp/ledger.ncu-rep --page raw --csv > gpurun_out/ledger_raw.csv 2>/dev/null
+      sz=$(stat -c %s /tmp/ledger.ncu-rep 2>/dev/null || echo 0)
+      if [ "$sz" -lt 30000000 ]; then cp /tmp/ledger.ncu-rep gpurun_out/ledger.ncu-rep; fi
+      wc -c gpurun_out/ledger_raw.csv ;;
+    ncu_one)
+      # full capture WITH source of one kernel: NCU_K=<regex> NCU_SCRIPT=<tools/x.py> NCU_ARGS=...
+      timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+          --profile-from-start off -k "regex:${NCU_K}" -c ${NCU_C:-1} -f -o gpurun_out/prof_${NCU_NAME:-one} \
+          python ${NCU_SCRIPT} ${NCU_ARGS} > gpurun_out/ncu_${NCU_NAME:-one}.log 2>&1
+      echo "== ncu_one rc=$?"; ls -la gpurun_out/prof_${NCU_NAME:-one}.ncu-rep ;;
     *)
       if [ -f "tools/$st" ]; then
         timeout 1200 python "tools/$st" > "gpurun_out/${st%.py}.log" 2>&1
