@@ -45,6 +45,22 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.5e-5,
+// far below the bf16 rounding P gets anyway).  On B200 MUFU.EX2 runs at 16 lanes/clk/SM: the 2 x 16K
+// exponentials of one KV block (two query tiles) take as long as its four 128x128x128 MMAs, so the
+// softmax warpgroups and the tensor pipe are co-limiting; moving every 4th exponential to the FMA
+// pipe takes the MUFU below the MMA time.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float xf = x + 12582912.f;          // 1.5 * 2^23: rounds x to an integer in the low mantissa bits
+  const float fr = x - (xf - 12582912.f);   // fractional part in [-0.5, 0.5]
+  float p = fmaf(fr, 0.0551716685f, 0.2426111251f);
+  p = fmaf(fr, p, 0.6932609677f);
+  p = fmaf(fr, p, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+}
+constexpr int kPolyEvery = 4;  // every kPolyEvery-th exponential of a row uses ex2_poly (0: none)
+
 struct Args2 {
   __nv_bfloat16* o;
   int64_t o_tok_stride, o_head_stride;
@@ -307,7 +323,9 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         float p[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float e = ex2f(__uint_as_float(r[i]) * a.scale_log2 - m_ref);
+          const float arg = __uint_as_float(r[i]) * a.scale_log2 - m_ref;
+          float e = (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) ? ex2_poly(arg)
+                                                                                              : ex2f(arg);
           if (need_mask) e = (kv0 + c * 32 + i <= kv_lim) ? e : 0.f;
           p[i] = e;
           rowsum += e;
