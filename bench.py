@@ -178,7 +178,7 @@ def decode_kernel_ledger(model, peaks, ctx=280):
     add("gemv qkv (+RMSNorm, +bias) N=%d K=%d" % (nq, lc.hidden_size), 2 * nq * lc.hidden_size,
         per_layer(lambda li, l: ops.gemv(x, l._qkv_w, bias=l._qkv_b, norm_w=l.input_layernorm.weight,
                                          norm_eps=lc.rms_norm_eps, out=qkv, static_w=True)))
-    add("decode_attn ctx=%d splits=%d (RoPE + KV append + split-KV)" % (ctx, dec.num_splits),
+    add("decode_attn ctx=%d splits=%d (RoPE + KV append + attention; 0 = one CTA per query head)" % (ctx, dec.num_splits),
         2 * 2 * (ctx + 1) * Hkv * D,
         per_layer(lambda li, l: ops.decode_attention(qkv, pos, cache.k(li), cache.v(li), cache.page_table,
                                                      xa, dec.ws, dec.counters, llm.inv_freq, Hq, Hkv, D,

@@ -205,7 +205,9 @@ typedef struct vila_decode_attn_params {
   float* ws;         /* >= Hkv*num_splits*G*(D+2) floats */
   int32_t* counters; /* Hkv ints, zero-initialised once */
   const float* inv_freq;
-  int32_t Hq, Hkv, D, num_splits;
+  int32_t Hq, Hkv, D, num_splits; /* num_splits 0: one CTA per query head, no split: the cache holds at
+                                     most 1024 tokens (page_table has >= 8 entries); 1..8: KV splits as a
+                                     thread-block cluster; 9..64: splits combined through ws/counters */
   float scale;
 } vila_decode_attn_params;
 int vila_decode_attention(const vila_decode_attn_params* p, void* stream);

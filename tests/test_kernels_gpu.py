@@ -538,6 +538,7 @@ def test_gemv_argmax_and_finalize(cuda):
 
 
 @pytest.mark.parametrize("ctx,splits", [(0, 1), (5, 1), (300, 4), (1000, 8), (130, 16),
+                                        (0, 0), (5, 0), (127, 0), (128, 0), (300, 0), (407, 0), (1023, 0),  # 0: one CTA per query head
                                         (16448, 37), (16448, 64), (65814, 37), (65814, 64), (4000, 8)])
 def test_decode_attention(cuda, ctx, splits):
     """(16448, *) / (65814, *): decode right after a 64-frame / 256-frame video prefill (README.md:69-70

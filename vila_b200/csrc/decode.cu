@@ -495,6 +495,165 @@ decode_attn_kernel(DecodeAttnParams p) {
 
 
 // ------------------------------------------------------------------------------------------------
+// decode attention, short contexts (<= 1024 cached tokens): ONE CTA per QUERY head over all tokens.
+// At the headline context (~300-400 tokens) the whole K/V of a layer is 0.6 MB: the op is a pure
+// latency chain, and the split-KV kernel above spends most of it combining partials (shared-memory
+// combine of 16 half-warps x 7 heads, two cluster barriers and a DSMEM pass).  Here a CTA owns one
+// query head: no cross-CTA combine, no cluster launch; the 7 heads of a GQA group re-read the same
+// K/V rows (L2 hits).  Token batches are register double-buffered so one L2 latency is exposed, not
+// one per batch; the page table (static across decode steps) is fetched before the PDL wait.
+// Same arithmetic as decode_attn_kernel (RoPE rounding points, bf16 probabilities, fp32 combine).
+// ------------------------------------------------------------------------------------------------
+constexpr int kDhThreads = 256;
+constexpr int kDhMaxPages = 8;  // <= 1024 tokens
+
+template <int D, int TB>
+__global__ void __launch_bounds__(kDhThreads)
+decode_attn_head_kernel(DecodeAttnParams p) {
+  static_assert(D == 128, "head_dim 128");
+  constexpr int VPT = 8, LPT = D / VPT;
+  const int h = blockIdx.x;
+  const int ratio = p.Hq / p.Hkv;
+  const int hk = h / ratio;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPT, dl = lane % LPT;
+  const int hw = warp * 2 + sub;  // 16 half-warps, one token each per step
+
+  __shared__ int pages_s[kDhMaxPages];
+  __shared__ float q_s[D];
+  __shared__ __align__(16) __nv_bfloat16 knew_s[D];
+  __shared__ __align__(16) __nv_bfloat16 vnew_s[D];
+  __shared__ float red_m[16], red_l[16];
+  __shared__ float red_o[16][D];
+
+  if (threadIdx.x < kDhMaxPages) pages_s[threadIdx.x] = p.page_table[threadIdx.x];  // static: before the wait
+  griddep_launch_dependents();
+  griddep_wait();
+  const int pos = *p.position;
+  const int n_tok = pos + 1;
+  __syncthreads();
+
+  auto load_batch = [&](int base, uint4* kr, uint4* vr) {
+#pragma unroll
+    for (int i = 0; i < TB; ++i) {
+      const int t = base + hw + 16 * i;
+      kr[i] = make_uint4(0, 0, 0, 0);
+      vr[i] = make_uint4(0, 0, 0, 0);
+      if (t < n_tok && t != pos) {
+        const size_t o = ((static_cast<size_t>(pages_s[t >> 7]) * 128 + (t & 127)) * p.Hkv + hk) * D + dl * VPT;
+        kr[i] = ldg_v4(p.k_pool + o);
+        vr[i] = ldg_v4(p.v_pool + o);
+      }
+    }
+  };
+  uint4 kA[TB], vA[TB], kB[TB], vB[TB];
+  load_batch(0, kA, vA);
+
+  // ---- RoPE of this query head and of the new key; stage in shared memory ----
+  if (threadIdx.x < D) {
+    const int i = threadIdx.x & (D / 2 - 1);
+    const bool is_k = threadIdx.x >= D / 2;
+    const __nv_bfloat16* src = is_k ? p.qkv + (p.Hq + hk) * D : p.qkv + h * D;
+    const float x0 = __bfloat162float(src[i]), x1 = __bfloat162float(src[i + D / 2]);
+    float sn, cs;
+    sincosf((float)pos * p.inv_freq[i], &sn, &cs);
+    cs = bf16_round(cs);
+    sn = bf16_round(sn);
+    const float y0 = bf16_round(bf16_round(x0 * cs) + bf16_round(-x1 * sn));
+    const float y1 = bf16_round(bf16_round(x1 * cs) + bf16_round(x0 * sn));
+    if (is_k) {
+      knew_s[i] = __float2bfloat16(y0);
+      knew_s[i + D / 2] = __float2bfloat16(y1);
+    } else {
+      q_s[i] = y0;
+      q_s[i + D / 2] = y1;
+    }
+  } else {
+    const int i = threadIdx.x - D;
+    vnew_s[i] = p.qkv[(p.Hq + p.Hkv + hk) * D + i];
+  }
+  __syncthreads();
+  if (h % ratio == 0) {  // KV append (DynamicCache.update), once per KV head
+    const size_t o = ((static_cast<size_t>(pages_s[pos >> 7]) * 128 + (pos & 127)) * p.Hkv + hk) * D;
+    if (threadIdx.x < D) p.k_pool[o + threadIdx.x] = knew_s[threadIdx.x];
+    else p.v_pool[o + threadIdx.x - D] = vnew_s[threadIdx.x - D];
+  }
+  float qreg[VPT];
+#pragma unroll
+  for (int e = 0; e < VPT; ++e) qreg[e] = q_s[dl * VPT + e];
+
+  float m = -INFINITY, l = 0.f, o_acc[VPT];
+#pragma unroll
+  for (int e = 0; e < VPT; ++e) o_acc[e] = 0.f;
+  const float sl2 = p.scale * 1.4426950408889634f;
+
+  auto consume = [&](int base, const uint4* kr, const uint4* vr) {
+#pragma unroll
+    for (int i = 0; i < TB; ++i) {
+      const int t = base + hw + 16 * i;
+      const bool valid = t < n_tok;
+      uint4 kv = kr[i], vv = vr[i];
+      if (valid && t == pos) {
+        kv = *reinterpret_cast<const uint4*>(knew_s + dl * VPT);
+        vv = *reinterpret_cast<const uint4*>(vnew_s + dl * VPT);
+      }
+      const float kf[VPT] = {bf_lo(kv.x), bf_hi(kv.x), bf_lo(kv.y), bf_hi(kv.y),
+                             bf_lo(kv.z), bf_hi(kv.z), bf_lo(kv.w), bf_hi(kv.w)};
+      const float vf[VPT] = {bf_lo(vv.x), bf_hi(vv.x), bf_lo(vv.y), bf_hi(vv.y),
+                             bf_lo(vv.z), bf_hi(vv.z), bf_lo(vv.w), bf_hi(vv.w)};
+      float sc = 0.f;
+#pragma unroll
+      for (int e = 0; e < VPT; ++e) sc = fmaf(qreg[e], kf[e], sc);
+#pragma unroll
+      for (int o = LPT / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+      if (valid) {
+        sc *= sl2;
+        const float m_new = fmaxf(m, sc);
+        const float alpha = exp2f(m - m_new);
+        const float pexp = exp2f(sc - m_new);
+        l = l * alpha + pexp;
+        const float pb = bf16_round(pexp);  // probabilities are cast to bf16 before P.V
+#pragma unroll
+        for (int e = 0; e < VPT; ++e) o_acc[e] = o_acc[e] * alpha + pb * vf[e];
+        m = m_new;
+      }
+    }
+  };
+  constexpr int STEP = 16 * TB;
+  for (int base = 0; base < n_tok; base += 2 * STEP) {  // block-uniform trip count
+    if (base + STEP < n_tok) load_batch(base + STEP, kB, vB);
+    consume(base, kA, vA);
+    if (base + STEP < n_tok) {
+      if (base + 2 * STEP < n_tok) load_batch(base + 2 * STEP, kA, vA);
+      consume(base + STEP, kB, vB);
+    }
+  }
+
+  // ---- combine the 16 half-warp partials (fixed order) ----
+  if (dl == 0) {
+    red_m[hw] = m;
+    red_l[hw] = l;
+  }
+#pragma unroll
+  for (int e = 0; e < VPT; ++e) red_o[hw][dl * VPT + e] = o_acc[e];
+  __syncthreads();
+  if (threadIdx.x < D) {
+    const int d = threadIdx.x;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) mm = fmaxf(mm, red_m[s]);
+    float ll = 0.f, oo = 0.f;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      const float w = (red_m[s] == -INFINITY) ? 0.f : exp2f(red_m[s] - mm);
+      ll += red_l[s] * w;
+      oo += red_o[s][d] * w;
+    }
+    p.out[h * D + d] = __float2bfloat16(oo / ll);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // long-context decode attention: combine of the split-KV partials written by fmha_decode_split
 // (tcgen05 FMHA kernel in split mode).  out[h, :] = sum_s w_s * O_s[h, :], w_s = 2^(lse_s - max) / sum.
 // Splits are summed in index order (deterministic).
@@ -564,8 +723,13 @@ int argmax_finalize(unsigned long long* key, int32_t* token_out, int32_t* token_
 int decode_attention(const DecodeAttnParams& p, cudaStream_t stream) {
   VB_CHECK(p.D == 128, "decode_attention: head_dim must be 128 (got %d)", p.D);
   VB_CHECK(p.Hq % p.Hkv == 0, "decode_attention: Hq %% Hkv != 0");
-  VB_CHECK(p.num_splits >= 1 && p.num_splits <= 64, "decode_attention: bad num_splits %d",
+  VB_CHECK(p.num_splits >= 0 && p.num_splits <= 64, "decode_attention: bad num_splits %d",
            p.num_splits);
+  if (p.num_splits == 0) {
+    // one CTA per query head, no split: contexts of at most 1024 tokens (8 pages), see the kernel
+    VB_CUDA(launch_pdl(decode_attn_head_kernel<128, 4>, dim3(p.Hq), dim3(kDhThreads), 0, stream, p));
+    return 0;
+  }
   const int G = p.Hq / p.Hkv;
   dim3 grid(p.Hkv, p.num_splits);
 #define VB_DA_CASE(GG)                                                                          \

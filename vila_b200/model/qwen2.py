@@ -486,7 +486,7 @@ class GraphDecoder:
         self.max_new = max_new
         Hq, Hkv, D = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
         self._fixed_splits = num_splits
-        self.num_splits = num_splits or 8
+        self.num_splits = 8 if num_splits is None else num_splits
         self.x = torch.zeros(cfg.hidden_size, device=dev, dtype=dt)
         self.qkv = torch.zeros((Hq + 2 * Hkv) * D, device=dev, dtype=dt)
         self.attn = torch.zeros(Hq * D, device=dev, dtype=dt)
@@ -514,13 +514,16 @@ class GraphDecoder:
     LONG_CTX = 2048
 
     def pick_splits(self, ctx: int):
-        """-> (num_splits, split_tokens).  Short contexts: 8 splits = one thread-block cluster per KV
-        head of the SIMT kernel (DSMEM combine, lowest latency), split_tokens = 0.  Long contexts
+        """-> (num_splits, split_tokens).  Up to 1024 tokens: 0 = one CTA per query head, nothing to
+        combine (a pure latency chain at these sizes).  Up to 2048: 8 splits = one thread-block cluster
+        per KV head of the SIMT kernel (DSMEM combine), split_tokens = 0.  Long contexts
         (video: 16K-66K tokens = 34-135 MB of K/V per layer) are a bandwidth problem: the tcgen05 FMHA
         kernel in split-KV mode, one CTA per SM (Hkv * splits <= #SMs), every split a whole number of
         128-token pages and all splits of (nearly) equal length."""
-        if self._fixed_splits:
+        if self._fixed_splits is not None:
             return self._fixed_splits, 0
+        if ctx <= 1024:
+            return 0, 0   # one CTA per query head, no split / combine (decode_attn_head_kernel)
         if ctx <= self.LONG_CTX:
             return 8, 0
         Hkv = self.llm.config.num_key_value_heads
