@@ -204,7 +204,8 @@ def test_linear_swiglu(cuda):
 # ------------------------------------------------------------------------------------------------
 # norms
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,cols", [(1024, 1152), (256, 4608), (7, 13824), (121, 3456)])
+@pytest.mark.parametrize("rows,cols", [(1024, 1152), (256, 4608), (7, 13824), (121, 3456),
+                                       (16384, 1152), (8195, 144), (9000, 2048), (8192, 2056)])  # >= 8192 rows: warp-per-row kernel (cols <= 2048)
 def test_layernorm(cuda, rows, cols):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(rows + cols)
@@ -216,7 +217,8 @@ def test_layernorm(cuda, rows, cols):
     assert rel_err(out, ref) < 5e-3
 
 
-@pytest.mark.parametrize("rows,cols", [(280, 3584), (1, 3584), (33, 2048)])
+@pytest.mark.parametrize("rows,cols", [(280, 3584), (1, 3584), (33, 2048),
+                                       (16470, 3584), (8193, 2048), (8200, 4096), (8192, 512)])  # >= 8192 rows: warp-per-row kernel
 def test_rmsnorm(cuda, rows, cols):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(rows + cols)
