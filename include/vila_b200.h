@@ -156,6 +156,12 @@ int vila_embed_splice(const void* table, const void* media, const int32_t* src, 
 int vila_rope_kv_append(void* qkv, const int32_t* positions, int S, int Hq, int Hkv, int D,
                         const float* inv_freq, void* k_pool, void* v_pool,
                         const int32_t* page_table, int cache_pos0, void* stream);
+/* (cache_pos0 < 0: the cache slot of row s is positions[s] itself — decode, position on the device) */
+/* vila_rope_kv_append with cos / sin taken from vila_rope_table(positions) (computed once per request
+ * and shared by all layers and heads; 16-byte accesses): the long-prefill form, bit-identical. */
+int vila_rope_kv_append_table(void* qkv, const void* rope_table, int S, int Hq, int Hkv, int D,
+                              void* k_pool, void* v_pool, const int32_t* page_table, int cache_pos0,
+                              void* stream);
 /* Fused q/k/v projection for a short prefill chunk (M <= 384 tokens, head_dim 128):
  * qkv = x @ w^T + bias; RoPE on the q and k heads; q heads -> qkv_out[:, :Hq*128]; k / v heads ->
  * the paged pools (k_pool NULL: they stay in qkv_out) — vila_linear followed by vila_rope_kv_append

@@ -473,6 +473,15 @@ def test_rope_kv_append(cuda):
     v = qkv[:, (Hq + Hkv) * D:].view(S, Hkv, D)
     assert torch.equal(v_pool[3, 100:128], v[:28]) and torch.equal(v_pool[1, :9], v[28:])
     assert torch.equal(k_pool[3, 100:128], got_k.transpose(0, 1)[:28])
+    # table-driven vectorised variant (long prefills): bit-identical, qkv and both pools
+    k2, v2, work2 = torch.zeros_like(k_pool), torch.zeros_like(v_pool), qkv.clone()
+    ops.rope_kv_append_table(work2, ops.rope_table(pos, D, inv), Hq, Hkv, D, k2, v2, pt, cache_pos0=100)
+    assert torch.equal(work2, work) and torch.equal(k2, k_pool) and torch.equal(v2, v_pool)
+    # decode form: cache slot = the position itself (cache_pos0 < 0), one row
+    k3, v3 = torch.zeros_like(k_pool), torch.zeros_like(v_pool)
+    one = qkv[:1].clone()
+    ops.rope_kv_append(one, torch.tensor([130], dtype=torch.int32, device=cuda), Hq, Hkv, D, inv, k3, v3, pt, cache_pos0=-1)
+    assert k3[1, 2].abs().sum() > 0 and v3[1, 2].abs().sum() > 0 and k3[3].abs().sum() == 0
 
 
 # ------------------------------------------------------------------------------------------------

@@ -94,6 +94,8 @@ SIGNATURES = {
     "vila_embed_splice": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "vila_rope_kv_append": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_int, c_void_p],
+    "vila_rope_kv_append_table": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_void_p],
     "vila_linear_qkv_rope": [c_void_p, C.c_int64, c_void_p, C.c_int64, c_void_p, c_void_p, C.c_int64,
                              c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_int, c_int, c_void_p],

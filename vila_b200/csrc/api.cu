@@ -182,6 +182,14 @@ int vila_rope_kv_append(void* qkv, const int32_t* positions, int S, int Hq, int 
                             page_table, cache_pos0, st(stream));
 }
 
+int vila_rope_kv_append_table(void* qkv, const void* rope_table, int S, int Hq, int Hkv, int D,
+                              void* k_pool, void* v_pool, const int32_t* page_table, int cache_pos0,
+                              void* stream) {
+  VB_REQUIRE_DEVICE();
+  return vb::rope_kv_append_table(mb(qkv), cb(rope_table), S, Hq, Hkv, D, mb(k_pool), mb(v_pool),
+                                  page_table, cache_pos0, st(stream));
+}
+
 int vila_linear_qkv_rope(const void* x, int64_t ldx, const void* w, int64_t ldw, const void* bias,
                          void* qkv_out, int64_t ldo, int M, int K, int Hq, int Hkv, int D,
                          const void* rope_table, void* k_pool, void* v_pool,

@@ -116,6 +116,11 @@ int rope_kv_append(__nv_bfloat16* qkv, const int32_t* positions, int S, int Hq, 
                    const float* inv_freq, __nv_bfloat16* k_pool, __nv_bfloat16* v_pool,
                    const int32_t* page_table, int cache_pos0, cudaStream_t stream);
 
+// same with cos / sin read from rope_table(positions) (long prefills; bit-identical)
+int rope_kv_append_table(__nv_bfloat16* qkv, const __nv_bfloat16* table, int S, int Hq, int Hkv, int D,
+                         __nv_bfloat16* k_pool, __nv_bfloat16* v_pool, const int32_t* page_table,
+                         int cache_pos0, cudaStream_t stream);
+
 // ---- decode (M == 1) ----------------------------------------------------------------------------
 struct GemvParams {
   const __nv_bfloat16* x;       // [K]

@@ -202,7 +202,8 @@ class Qwen2ForCausalLM(nn.Module):
             position_ids = position_ids.to(device=self.device, dtype=torch.int32).contiguous()
         x = inputs_embeds.to(self.dtype).contiguous().clone()
         fused_rope = D == 128 and 0 < S <= 384
-        table = ops.rope_table(position_ids, D, self.inv_freq) if fused_rope else None
+        # cos / sin once per request (shared by all layers and heads)
+        table = ops.rope_table(position_ids, D, self.inv_freq) if S > 0 and D % 16 == 0 else None
         for li, layer in enumerate(self.model.layers):
             h = ops.rmsnorm(x, layer.input_layernorm.weight, cfg.rms_norm_eps)
             # short chunks: projection + RoPE + cache append in one kernel; else two kernels
@@ -210,8 +211,12 @@ class Qwen2ForCausalLM(nn.Module):
                                       cache.v(li), cache.page_table, p0, static_w=True) if fused_rope else None
             if qkv is None:
                 qkv = ops.linear(h, layer._qkv_w, layer._qkv_b, static_w=True)
-                ops.rope_kv_append(qkv, position_ids, Hq, Hkv, D, self.inv_freq, cache.k(li),
-                                   cache.v(li), cache.page_table, p0)
+                if table is not None:
+                    ops.rope_kv_append_table(qkv, table, Hq, Hkv, D, cache.k(li), cache.v(li),
+                                             cache.page_table, p0)
+                else:
+                    ops.rope_kv_append(qkv, position_ids, Hq, Hkv, D, self.inv_freq, cache.k(li),
+                                       cache.v(li), cache.page_table, p0)
             q = qkv.view(S, Hq + 2 * Hkv, D)[:, :Hq]
             attn = ops.fmha(q, cache.k(li), cache.v(li), B=1, Sq=S, Sk=p0 + S, causal=True,
                             scale=D ** -0.5, page_table=cache.page_table)

@@ -265,6 +265,19 @@ def rope_kv_append(qkv: torch.Tensor, positions: torch.Tensor, Hq: int, Hkv: int
                                           _stream()), "vila_rope_kv_append")
 
 
+def rope_kv_append_table(qkv: torch.Tensor, table: torch.Tensor, Hq: int, Hkv: int, D: int,
+                         k_pool: Optional[torch.Tensor] = None, v_pool: Optional[torch.Tensor] = None,
+                         page_table: Optional[torch.Tensor] = None, cache_pos0: int = 0) -> None:
+    """rope_kv_append with the cos | sin table of rope_table(positions) (long prefills)."""
+    _chk(qkv, "qkv"); _chk(table, "table")
+    assert qkv.is_contiguous() and qkv.shape[-1] == (Hq + 2 * Hkv) * D
+    S = qkv.shape[0]
+    assert table.shape == (S, D) and table.is_contiguous()
+    check(_lib.load().vila_rope_kv_append_table(_p(qkv), _p(table), S, Hq, Hkv, D, _p(k_pool), _p(v_pool),
+                                                _p(page_table), cache_pos0, _stream()),
+          "vila_rope_kv_append_table")
+
+
 def rope_table(positions: torch.Tensor, D: int, inv_freq: torch.Tensor) -> torch.Tensor:
     """cos | sin table [S, D] bf16 of a request's positions (shared by all layers and heads)."""
     assert positions.dtype == torch.int32 and inv_freq.dtype == torch.float32 and positions.is_cuda

@@ -179,15 +179,14 @@ class SequenceParallelPrefill:
         x = local_embeds.to(llm.dtype).contiguous().clone()
         n_local_pages = 2 * cp
         compute = torch.cuda.current_stream()
+        table = ops.rope_table(positions, D, llm.inv_freq)  # cos | sin of the GLOBAL positions, once
         for li, layer in enumerate(llm.model.layers):
             h = ops.rmsnorm(x, layer.input_layernorm.weight, cfg.rms_norm_eps)
             qkv = ops.linear(h, layer._qkv_w, layer._qkv_b, static_w=True)
             kpool, vpool = pool[li, 0], pool[li, 1]
             # RoPE with GLOBAL positions; K/V rows land in this rank's region of the pool
-            ops.rope_kv_append(qkv[:c], positions[:c], Hq, Hkv, D, llm.inv_freq, kpool, vpool,
-                               page_table, a0)
-            ops.rope_kv_append(qkv[c:], positions[c:], Hq, Hkv, D, llm.inv_freq, kpool, vpool,
-                               page_table, b0)
+            ops.rope_kv_append_table(qkv[:c], table[:c], Hq, Hkv, D, kpool, vpool, page_table, a0)
+            ops.rope_kv_append_table(qkv[c:], table[c:], Hq, Hkv, D, kpool, vpool, page_table, b0)
             q = qkv.view(2 * c, Hq + 2 * Hkv, D)[:, :Hq]
             attn = torch.empty(2 * c, Hq, D, dtype=llm.dtype, device=llm.device)
             if self.world > 1:
