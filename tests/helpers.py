@@ -53,7 +53,7 @@ def _record(row: dict) -> None:
 
 
 def check_close(name: str, got: torch.Tensor, truth: torch.Tensor, ref_lowp: torch.Tensor = None,
-                rel_floor: float = 1e-3, factor: float = 2.0) -> float:
+                rel_floor: float = 1e-3, factor: float = 1.6) -> float:
     """Tolerance model for bf16 kernels (stated once here, used by every e2e parity test):
 
         err(got) <= factor * err(reference's own bf16 path) + rel_floor * max|truth|
@@ -62,6 +62,9 @@ def check_close(name: str, got: torch.Tensor, truth: torch.Tensor, ref_lowp: tor
     the reference's rounding points (unfused torch ops).  I.e. the CUDA path may not be further from
     the fp32 truth than `factor` x the reference's own bf16 noise (+1e-3 relative).  Without `ref_lowp`
     the bound is 2^-7 relative (one bf16 ulp of the largest value) + rel_floor.
+    factor: 1.6 by default — measured ratios on B200 (profiles/r02_parity.md) are 0.87-1.10 on the
+    full-size configurations and up to 1.29 on the tiny test architecture (few elements: the max is
+    noisy); the full-size tests pass factor=1.3.
     Every call prints and records err, ref_err and their ratio (north_star's "1e-3" is not reachable
     by ANY bf16 pipeline — the reference's own bf16 path misses it — so the ratio to the reference's
     noise is the number to watch: 1.0 = as close to the fp32 truth as the reference itself)."""

@@ -93,14 +93,14 @@ def test_cfg2_matches_oracle_full_depth(cuda):
     pxd = px.cuda()
     feats = model.vision_tower(pxd[None]).clone()
     t32 = o32.tower(pxd[None].float())
-    check_close("cfg2 tower (26 layers, 1x448^2)", feats, t32, o16.tower(pxd[None]))
+    check_close("cfg2 tower (26 layers, 1x448^2)", feats, t32, o16.tower(pxd[None]), factor=1.3)
     enc = model.encode_images(pxd[None]).clone()
-    check_close("cfg2 tower+projector", enc, o32.project(t32), o16.encode_images(pxd[None]))
+    check_close("cfg2 tower+projector", enc, o32.project(t32), o16.encode_images(pxd[None]), factor=1.3)
     out = model(input_ids=ids, media={"image": [pxd]})
     truth = o32.forward_logits(ids, [pxd.float()])
     assert out.logits.shape[1:] == truth.shape == (279, cfg.llm_cfg.vocab_size)
     check_close("cfg2 logits [279 x 152064] (28 layers)", out.logits[0], truth,
-                o16.forward_logits(ids, [pxd]))
+                o16.forward_logits(ids, [pxd]), factor=1.3)
     new = model.generate(input_ids=ids, media={"image": [pxd]}, max_new_tokens=24, eos_token_id=None)
     want, logits = o32.generate(ids, [pxd.float()], 24)
     greedy_ids_match(new[0].tolist(), want, logits, 3 * 2 ** -8 * logits.abs().max().item())
@@ -163,10 +163,10 @@ def test_cfg3_matches_oracle_full_depth(cuda):
     feats = model.vision_tower(frames).clone()
     t32 = o32.tower(frames.float())
     t16 = o16.tower(frames)
-    check_close("cfg3 tower (26 layers, 64 frames)", feats, t32, t16)
+    check_close("cfg3 tower (26 layers, 64 frames)", feats, t32, t16, factor=1.3)
     enc = model.encode_images(frames).clone()
     p32 = o32.project(t32)
-    check_close("cfg3 tower+projector (2x2_fix)", enc, p32, o16.project(t16))
+    check_close("cfg3 tower+projector (2x2_fix)", enc, p32, o16.project(t16), factor=1.3)
     del t32, t16, feats
     from oracle import vila_oracle as O
     table = model.llm.model.embed_tokens.weight
@@ -183,8 +183,8 @@ def test_cfg3_matches_oracle_full_depth(cuda):
     lg = llm.logits_from_hidden(hid[-1:])
     l32, _, h32 = O.qwen2_forward(seq.float(), o32.llm, o32.lcfg, last_only=True, return_hidden=True)
     l16, _, h16 = O.qwen2_forward(seq, o16.llm, o16.lcfg, last_only=True, return_hidden=True)
-    check_close("cfg3 prefill hidden [16470 x 3584] (28 layers)", hid, h32, h16)
-    check_close("cfg3 last-token logits", lg, l32, l16)
+    check_close("cfg3 prefill hidden [16470 x 3584] (28 layers)", hid, h32, h16, factor=1.3)
+    check_close("cfg3 last-token logits", lg, l32, l16, factor=1.3)
 
 
 def test_cfg4_dynamic_s2_full_size(cuda):
@@ -221,11 +221,11 @@ def test_cfg4_matches_oracle_full_depth(cuda):
     t32 = o32.encode_images(tiles.float(), [bs])
     t16 = o16.encode_images(tiles, [bs])
     assert len(t32) == 1 and got[0].shape == t32[0].shape
-    check_close("cfg4 dynamic-S2 encode_images (35 tiles, C=3456)", got[0], t32[0], t16[0])
+    check_close("cfg4 dynamic-S2 encode_images (35 tiles, C=3456)", got[0], t32[0], t16[0], factor=1.3)
     # single tile (block_size None) through the share-tile path
     one = model.encode_images(tiles[:1], block_sizes=[None])
     check_close("cfg4 dynamic-S2 single tile", one[0], o32.encode_images(tiles[:1].float(), [None])[0],
-                o16.encode_images(tiles[:1], [None])[0])
+                o16.encode_images(tiles[:1], [None])[0], factor=1.3)
     # fp32 / fp16 pixels (media._to_tensor gives fp32; the reference calls .half())
     for dt in (torch.float32, torch.float16):
         again = model.encode_images(tiles[:1].to(dt), block_sizes=[None])
@@ -246,11 +246,11 @@ def test_cfg1_lite3b_matches_oracle_full_depth(cuda):
     enc = model.encode_images(px[None]).clone()
     assert enc.shape == (1, 121, cfg.hidden_size)
     check_close("cfg1 tower+projector (3x3_fix)", enc, o32.encode_images(px[None].float()),
-                o16.encode_images(px[None]))
+                o16.encode_images(px[None]), factor=1.3)
     out = model(input_ids=ids, media={"image": [px]})
     truth = o32.forward_logits(ids, [px.float()])
     assert out.logits.shape[1] == truth.shape[0] == 22 + 122
-    check_close("cfg1 logits (36 layers)", out.logits[0], truth, o16.forward_logits(ids, [px]))
+    check_close("cfg1 logits (36 layers)", out.logits[0], truth, o16.forward_logits(ids, [px]), factor=1.3)
     new = model.generate(input_ids=ids, media={"image": [px]}, max_new_tokens=32, eos_token_id=None)
     want, logits = o32.generate(ids, [px.float()], 32)
     greedy_ids_match(new[0].tolist(), want, logits, 3 * 2 ** -8 * logits.abs().max().item())
