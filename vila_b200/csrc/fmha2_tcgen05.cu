@@ -59,7 +59,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(fr, p, 0.9999280572f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
 }
-constexpr int kPolyEvery = 4;  // every kPolyEvery-th exponential of a row uses ex2_poly (0: none)
+// kPoly (template parameter): every kPoly-th exponential of a row uses ex2_poly (0: none)
 
 struct Args2 {
   __nv_bfloat16* o;
@@ -70,7 +70,7 @@ struct Args2 {
   float scale_log2;
 };
 
-template <int DP, int CW>
+template <int DP, int CW, int kPolyEvery>
 __global__ void __launch_bounds__(kThreads2, 1)
 fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, Args2 a) {
@@ -228,24 +228,18 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
       ring_release(0);
       for (int j = 0; j < nmax; ++j) {
+        // S(j+1) BEFORE PV(j): the softmax warpgroups release the S buffer as soon as they hold block
+        // j's scores in registers, so the tensor pipe computes Q K(j+1)^T while they exponentiate
+        if (j + 1 < nmax) {
+          ring_wait(2 * (j + 1));                   // K(j+1)
+          for (int t = 0; t < 2; ++t)
+            if (j + 1 < nblk[t]) issue_s(t, j + 1);
+          ring_release(2 * (j + 1));
+        }
         ring_wait(2 * j + 1);                       // V(j)
-        const bool more = (j + 1 < nmax);
-        bool k_waited = false;
-        for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < 2; ++t)
           if (j < nblk[t]) issue_pv(t, j);
-          if (j + 1 < nblk[t]) {
-            if (!k_waited) {
-              ring_wait(2 * (j + 1));               // K(j+1)
-              k_waited = true;
-            }
-            issue_s(t, j + 1);
-          }
-        }
-        ring_release(2 * j + 1);                    // V(j) consumed by every PV issued above
-        if (more) {
-          if (!k_waited) ring_wait(2 * (j + 1));    // (cannot happen: nmax = max(nblk))
-          ring_release(2 * (j + 1));                // K(j+1) consumed by every S issued above
-        }
+        ring_release(2 * j + 1);
       }
     }
   } else {
@@ -273,20 +267,21 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const bool need_mask = (kv0 + BKV > a.Sk) || (a.causal && (kv0 + BKV - 1 > qt * BQ + off));
       const int kv_lim = a.causal ? min(a.Sk - 1, q_idx + off) : a.Sk - 1;
 
+      // the whole 128-column score row of this thread in registers with ONE TMEM round trip, then the
+      // S buffer goes back to the tensor pipe (was: two passes of four dependent 32-column loads)
+      uint32_t r[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, r + c * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[t]);
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(s_addr + c * 32, r);
-        tmem_ld_wait();
-        if (need_mask) {
+      if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            mx = fmaxf(mx, (kv0 + c * 32 + i <= kv_lim) ? __uint_as_float(r[i]) : -INFINITY);
-        } else {
+        for (int i = 0; i < BKV; ++i) mx = fmaxf(mx, (kv0 + i <= kv_lim) ? __uint_as_float(r[i]) : -INFINITY);
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
+        for (int i = 0; i < BKV; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
       }
       const float m_blk = mx * a.scale_log2;
       if (j == 0) {
@@ -315,15 +310,12 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
       mbar_wait(&p_free[t], (j & 1) ^ 1);
       float rowsum = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(s_addr + c * 32, r);
-        tmem_ld_wait();
         float p[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float arg = __uint_as_float(r[i]) * a.scale_log2 - m_ref;
+          const float arg = __uint_as_float(r[c * 32 + i]) * a.scale_log2 - m_ref;
           float e = (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) ? ex2_poly(arg)
                                                                                               : ex2f(arg);
           if (need_mask) e = (kv0 + c * 32 + i <= kv_lim) ? e : 0.f;
@@ -346,7 +338,6 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
-      mbar_arrive(&s_free[t]);
     }
 
     if (n > 0) {
@@ -385,7 +376,7 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   }
 }
 
-template <int DP, int CW>
+template <int DP, int CW, int kPolyEvery>
 int launch_fmha2(const FmhaParams& p, cudaStream_t stream) {
   using C = Cfg2<DP, CW>;
   CUtensorMap tq, tk, tv;
@@ -421,7 +412,7 @@ int launch_fmha2(const FmhaParams& p, cudaStream_t stream) {
   a.causal = p.causal;
   a.paged = paged ? 1 : 0;
   a.scale_log2 = p.scale * 1.4426950408889634f;
-  auto kern = fmha2_fwd_kernel<DP, CW>;
+  auto kern = fmha2_fwd_kernel<DP, CW, kPolyEvery>;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
@@ -435,9 +426,17 @@ int launch_fmha2(const FmhaParams& p, cudaStream_t stream) {
 }  // namespace
 
 // returns -1 when the shape is not handled by v2 (caller uses v1)
-int fmha_prefill_v2(const FmhaParams& p, cudaStream_t stream) {
-  if (p.D == 128) return launch_fmha2<128, 64>(p, stream);
-  if (p.D <= 96 && p.D > 64) return launch_fmha2<96, 32>(p, stream);
+int fmha_prefill_v2(const FmhaParams& p, cudaStream_t stream, int poly_every) {
+  if (p.D == 128) {
+    if (poly_every == 0) return launch_fmha2<128, 64, 0>(p, stream);
+    if (poly_every == 2) return launch_fmha2<128, 64, 2>(p, stream);
+    return launch_fmha2<128, 64, 4>(p, stream);
+  }
+  if (p.D <= 96 && p.D > 64) {
+    if (poly_every == 0) return launch_fmha2<96, 32, 0>(p, stream);
+    if (poly_every == 2) return launch_fmha2<96, 32, 2>(p, stream);
+    return launch_fmha2<96, 32, 4>(p, stream);
+  }
   return -1;
 }
 

@@ -457,8 +457,11 @@ int fmha_decode_split(const FmhaParams& p, const int32_t* n_tok_minus_1, int spl
 
 // variant: 0 = size heuristic, 1 = force the one-tile-per-CTA kernel, 2 = force the two-tile kernel
 // (falls through to v1 only when v2 does not cover the head dim / Sq <= 128).
-int fmha_prefill_cfg(int variant, const FmhaParams& p, cudaStream_t stream) {
-  VB_CHECK(variant >= 0 && variant <= 2, "fmha: unknown variant %d", variant);
+int fmha_prefill_cfg(int variant_in, const FmhaParams& p, cudaStream_t stream) {
+  int variant = variant_in;
+  VB_CHECK(variant >= 0 && variant <= 4, "fmha: unknown variant %d", variant);
+  const int poly = variant == 3 ? 0 : (variant == 4 ? 2 : 4);  // 3 / 4: two-tile kernel with no / half polynomial exp2
+  if (variant >= 3) variant = 2;
   VB_CHECK(p.B > 0 && p.Sq > 0 && p.Sk > 0, "fmha: empty problem");
   VB_CHECK(p.Hq % p.Hkv == 0, "fmha: Hq (%d) must be a multiple of Hkv (%d)", p.Hq, p.Hkv);
   VB_CHECK(p.D % 8 == 0, "fmha: head dim must be a multiple of 8 (got %d)", p.D);
@@ -474,7 +477,7 @@ int fmha_prefill_cfg(int variant, const FmhaParams& p, cudaStream_t stream) {
     const bool use_v2 = variant == 2 ? p.Sq > 128
                                      : (variant == 1 ? false : (p.Sq > 128 && v2_ctas >= num_sms()));
     if (use_v2) {
-      const int rc = fmha_prefill_v2(p, stream);
+      const int rc = fmha_prefill_v2(p, stream, poly);
       if (rc >= 0) return rc;
       VB_CHECK(variant != 2, "fmha: the two-tile kernel does not cover head dim %d", p.D);
     }
