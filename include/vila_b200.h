@@ -114,7 +114,7 @@ int vila_fmha(const vila_fmha_params* p, void* stream);
 /* test hook (like vila_linear_cfg): same, forcing the kernel flavour instead of the size heuristic:
  *   0 heuristic; 1 one query tile per CTA (fmha_fwd_kernel); 2 two query tiles per CTA with ping-pong
  *   softmax warpgroups and the O accumulator in TMEM (fmha2_fwd_kernel; needs Sq > 128, D in 72..96 or 128);
- *   3 / 4: as 2 with none / every 2nd exponential on the FMA pipe (2 = every 4th) */
+ *   3 / 4: as 2 with every 4th / every 2nd exponential as an FMA-pipe polynomial (measured slower) */
 int vila_fmha_cfg(int variant, const vila_fmha_params* p, void* stream);
 
 /* im2col for Conv2d(3,1152,k=14,s=14) (modeling_siglip.py:269-275): pixels [B,C,H,W] ->

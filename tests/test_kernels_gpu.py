@@ -373,7 +373,7 @@ def test_fmha2_lazy_rescale_growing_maxima(cuda):
         k = bf(torch.randn(S, Hkv, D, device=cuda, generator=g) * ramp)
         v = bf(torch.randn(S, Hkv, D, device=cuda, generator=g))
         ref = ref_attention(q[None], k[None], v[None], causal, D ** -0.5)[0]
-        for variant in (1, 2, 3, 4):  # 3 / 4: two-tile kernel with no / every-2nd polynomial exp2
+        for variant in (1, 2, 3, 4):  # 3 / 4: two-tile kernel with every 4th / 2nd exp2 as a polynomial
             out = ops.fmha(q, k, v, B=1, Sq=S, Sk=S, causal=causal, scale=D ** -0.5, variant=variant)
             assert torch.isfinite(out.float()).all()
             report_rel(f"fmha{variant} growing maxima d={D}", out, ref, 1.5e-2)

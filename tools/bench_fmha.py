@@ -15,7 +15,7 @@ def timeit(fn, reps=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3 / reps
 res = {}
-for variant, tag in ((1, "v1"), (2, "v2_poly4"), (3, "v2_poly0"), (4, "v2_poly2")):
+for variant, tag in ((1, "v1"), (2, "v2"), (3, "v2_poly4")):
   for name, (B, S, H, Hkv, D, causal) in {"vit_1tile": (1, 1024, 16, 16, 72, False), "vit_64": (64, 1024, 16, 16, 72, False),
                                         "llm_279": (1, 279, 28, 4, 128, True), "llm_4k": (1, 4096, 28, 4, 128, True),
                                         "llm_16k": (1, 16470, 28, 4, 128, True),

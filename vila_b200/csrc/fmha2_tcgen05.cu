@@ -59,7 +59,30 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(fr, p, 0.9999280572f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
 }
-// kPoly (template parameter): every kPoly-th exponential of a row uses ex2_poly (0: none)
+// kPolyEvery (template parameter): every n-th exponential of a row uses ex2_poly (0: none).  MEASURED
+// (tools/bench_fmha.py, S = 65.8K causal): 0 -> 963 TF/s, 4 -> 884, 2 -> 830: the softmax warps are
+// issue-slot bound as much as MUFU bound, the ~10-instruction polynomial costs more than it frees.
+// It stays as a selectable flavour (vila_fmha_cfg 3 / 4); the default is 0.
+
+// Blackwell packed fp32 (two lanes per instruction: FFMA2 / FADD2) and 3-input max (FMNMX3): the
+// softmax loop is issue-slot bound, these halve its arithmetic instruction count.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%4}; mov.b64 rc, {%5,%5}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {
+  asm("{.reg .b64 ra, rd; mov.b64 ra, {%2,%3}; mov.b64 rd, {%0,%1}; add.rn.f32x2 rd, rd, ra; "
+      "mov.b64 {%0,%1}, rd;}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 
 struct Args2 {
   __nv_bfloat16* o;
@@ -280,8 +303,16 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
         for (int i = 0; i < BKV; ++i) mx = fmaxf(mx, (kv0 + i <= kv_lim) ? __uint_as_float(r[i]) : -INFINITY);
       } else {
+        // four independent max chains (two warps per scheduler: little latency hiding, so the
+        // dependent chains of the row reductions are kept short)
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < BKV; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < BKV; i += 8) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            m4[q] = fmax3(m4[q], __uint_as_float(r[i + 2 * q]), __uint_as_float(r[i + 2 * q + 1]));
+        }
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
       const float m_blk = mx * a.scale_log2;
       if (j == 0) {
@@ -309,18 +340,30 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
 
       mbar_wait(&p_free[t], (j & 1) ^ 1);
-      float rowsum = 0.f;
+      float rowsum = 0.f, rowsum1 = 0.f, rs2 = 0.f, rs3 = 0.f;  // 4 independent accumulation chains
+      const float neg_m = -m_ref;
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) {
         float p[32];
+        if (need_mask) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float arg = __uint_as_float(r[c * 32 + i]) * a.scale_log2 - m_ref;
-          float e = (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) ? ex2_poly(arg)
-                                                                                              : ex2f(arg);
-          if (need_mask) e = (kv0 + c * 32 + i <= kv_lim) ? e : 0.f;
-          p[i] = e;
-          rowsum += e;
+          for (int i = 0; i < 32; ++i) {
+            const float arg = __uint_as_float(r[c * 32 + i]) * a.scale_log2 - m_ref;
+            const float e = (kv0 + c * 32 + i <= kv_lim) ? ex2f(arg) : 0.f;
+            p[i] = e;
+            rowsum += e;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float a0, a1;
+            ffma2(a0, a1, __uint_as_float(r[c * 32 + i]), __uint_as_float(r[c * 32 + i + 1]), a.scale_log2, neg_m);
+            constexpr int kP = kPolyEvery > 0 ? kPolyEvery : 1;
+            p[i] = (kPolyEvery > 0 && (i % kP) == kP - 1) ? ex2_poly(a0) : ex2f(a0);
+            p[i + 1] = (kPolyEvery > 0 && ((i + 1) % kP) == kP - 1) ? ex2_poly(a1) : ex2f(a1);
+            if ((i & 2) == 0) fadd2(rowsum, rowsum1, p[i], p[i + 1]);
+            else fadd2(rs2, rs3, p[i], p[i + 1]);
+          }
         }
         uint8_t* prow = my_p + (c >> 1) * (BQ * 128) + row * 128;
 #pragma unroll
@@ -334,6 +377,7 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           *reinterpret_cast<uint4*>(prow + ((piece ^ (row & 7)) << 4)) = v4;
         }
       }
+      rowsum += rowsum1 + (rs2 + rs3);
       l += rowsum;
       fence_proxy_async_smem();
       tc_fence_before();
@@ -426,16 +470,16 @@ int launch_fmha2(const FmhaParams& p, cudaStream_t stream) {
 }  // namespace
 
 // returns -1 when the shape is not handled by v2 (caller uses v1)
-int fmha_prefill_v2(const FmhaParams& p, cudaStream_t stream, int poly_every) {
+int fmha_prefill_v2(const FmhaParams& p, cudaStream_t stream, int poly_every) {  // default 0, see kPolyEvery
   if (p.D == 128) {
-    if (poly_every == 0) return launch_fmha2<128, 64, 0>(p, stream);
+    if (poly_every == 4) return launch_fmha2<128, 64, 4>(p, stream);
     if (poly_every == 2) return launch_fmha2<128, 64, 2>(p, stream);
-    return launch_fmha2<128, 64, 4>(p, stream);
+    return launch_fmha2<128, 64, 0>(p, stream);
   }
   if (p.D <= 96 && p.D > 64) {
-    if (poly_every == 0) return launch_fmha2<96, 32, 0>(p, stream);
+    if (poly_every == 4) return launch_fmha2<96, 32, 4>(p, stream);
     if (poly_every == 2) return launch_fmha2<96, 32, 2>(p, stream);
-    return launch_fmha2<96, 32, 4>(p, stream);
+    return launch_fmha2<96, 32, 0>(p, stream);
   }
   return -1;
 }

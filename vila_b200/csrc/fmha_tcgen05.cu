@@ -48,6 +48,19 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%4}; mov.b64 rc, {%5,%5}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {
+  asm("{.reg .b64 ra, rd; mov.b64 ra, {%2,%3}; mov.b64 rd, {%0,%1}; add.rn.f32x2 rd, rd, ra; "
+      "mov.b64 {%0,%1}, rd;}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1));
+}
+
 struct FmhaKernelArgs {
   __nv_bfloat16* o;
   int64_t o_tok_stride, o_head_stride;
@@ -271,19 +284,29 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // pass 2: P = exp2(S*scale - m) -> bf16 -> swizzled smem (double-buffered: P_j is written
       // while the tensor core is still reading P_{j-1})
       mbar_wait(&p_free[s], ((j >> 1) & 1) ^ 1);
-      float rowsum = 0.f;
+      float rowsum = 0.f, rowsum1 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < BKV / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(s_addr + c * 32, r);
         tmem_ld_wait();
         float p[32];
+        if (need_mask) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = ex2(__uint_as_float(r[i]) * a.scale_log2 - m_use);
-          if (need_mask) e = (kv0 + c * 32 + i <= kv_lim) ? e : 0.f;
-          p[i] = e;
-          rowsum += e;
+          for (int i = 0; i < 32; ++i) {
+            const float e = (kv0 + c * 32 + i <= kv_lim) ? ex2(__uint_as_float(r[i]) * a.scale_log2 - m_use) : 0.f;
+            p[i] = e;
+            rowsum += e;
+          }
+        } else {  // packed fp32 (FFMA2 / FADD2): the softmax warps are issue-slot bound
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float a0, a1;
+            ffma2(a0, a1, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), a.scale_log2, -m_use);
+            p[i] = ex2(a0);
+            p[i + 1] = ex2(a1);
+            fadd2(rowsum, rowsum1, p[i], p[i + 1]);
+          }
         }
         uint8_t* prow = p_s + s * C::kPBytes + (c >> 1) * (BQ * 128) + row * 128;
 #pragma unroll
@@ -297,7 +320,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           *reinterpret_cast<uint4*>(prow + ((piece ^ (row & 7)) << 4)) = v4;
         }
       }
-      l = l * alpha + rowsum;
+      l = l * alpha + (rowsum + rowsum1);
       m = m_new;
       fence_proxy_async_smem();
       mbar_arrive(&p_full[s]);
@@ -460,7 +483,7 @@ int fmha_decode_split(const FmhaParams& p, const int32_t* n_tok_minus_1, int spl
 int fmha_prefill_cfg(int variant_in, const FmhaParams& p, cudaStream_t stream) {
   int variant = variant_in;
   VB_CHECK(variant >= 0 && variant <= 4, "fmha: unknown variant %d", variant);
-  const int poly = variant == 3 ? 0 : (variant == 4 ? 2 : 4);  // 3 / 4: two-tile kernel with no / half polynomial exp2
+  const int poly = variant == 3 ? 4 : (variant == 4 ? 2 : 0);  // 3 / 4: two-tile kernel with every 4th / 2nd exp2 as a polynomial
   if (variant >= 3) variant = 2;
   VB_CHECK(p.B > 0 && p.Sq > 0 && p.Sk > 0, "fmha: empty problem");
   VB_CHECK(p.Hq % p.Hkv == 0, "fmha: Hq (%d) must be a multiple of Hkv (%d)", p.Hq, p.Hkv);

@@ -66,8 +66,8 @@ struct FmhaParams {
 };
 int fmha_prefill(const FmhaParams& p, cudaStream_t stream);
 int fmha_prefill_cfg(int variant, const FmhaParams& p, cudaStream_t stream);  // 0 auto, 1 one-tile, 2 two-tile
-// poly_every: every n-th exponential on the FMA pipe (4 default; 0 none; 2 half) — test/bench hook
-int fmha_prefill_v2(const FmhaParams& p, cudaStream_t stream, int poly_every = 4);  // -1: shape not handled
+// poly_every: every n-th exponential on the FMA pipe (0 = none, the default; 4; 2) — test/bench hook
+int fmha_prefill_v2(const FmhaParams& p, cudaStream_t stream, int poly_every = 0);  // -1: shape not handled
 // split-KV mode of the one-tile kernel for decode at long context (see fmha_tcgen05.cu)
 int fmha_decode_split(const FmhaParams& p, const int32_t* n_tok_minus_1, int split_tokens,
                       float* o_partial, float* lse, cudaStream_t stream);

@@ -519,15 +519,16 @@ class GraphDecoder:
     LONG_CTX = 2048
 
     def pick_splits(self, ctx: int):
-        """-> (num_splits, split_tokens).  Up to 1024 tokens: 0 = one CTA per query head, nothing to
-        combine (a pure latency chain at these sizes).  Up to 2048: 8 splits = one thread-block cluster
+        """-> (num_splits, split_tokens).  Up to 512 tokens: 0 = one CTA per query head, nothing to
+        combine (a pure latency chain at these sizes; measured equal to the 8-split kernel at 280-410
+        tokens, slower at 1000: tools/bench_decode_attn.py).  Up to 2048: 8 splits = one thread-block cluster
         per KV head of the SIMT kernel (DSMEM combine), split_tokens = 0.  Long contexts
         (video: 16K-66K tokens = 34-135 MB of K/V per layer) are a bandwidth problem: the tcgen05 FMHA
         kernel in split-KV mode, one CTA per SM (Hkv * splits <= #SMs), every split a whole number of
         128-token pages and all splits of (nearly) equal length."""
         if self._fixed_splits is not None:
             return self._fixed_splits, 0
-        if ctx <= 1024:
+        if ctx <= 512:
             return 0, 0   # one CTA per query head, no split / combine (decode_attn_head_kernel)
         if ctx <= self.LONG_CTX:
             return 8, 0
