@@ -17,6 +17,8 @@ mm_projector -> text/media splice -> Qwen2-7B prefill (S = 257 visual + 22 text 
   ttft_roofline   flops / bytes / floor of the TTFT path and the achieved fraction
   video_decode    BASELINE configs[2] follow-up: 64-frame prefill (S = 16.5K) then 128 greedy tokens
                   through LlavaLlamaModel.generate: decode tok/s at ctx 16.5K with its HBM roofline
+  batched_decode  serving follow-up: 8 concurrent copies of the request, continuous batching over one
+                  shared paged pool (vila_b200/serving.py): aggregate tok/s
   sp_prefill      BASELINE configs[4]: LongVILA 256 frames (S = 65,814), sequence-parallel over ALL
                   ranks of this launch through LlavaLlamaModel.generate(max_new_tokens=1) with
                   vila_b200.sp enabled; first-token id + last-token logits top-5 / checksum so runs at
@@ -241,6 +243,48 @@ def video_decode_block(model, peaks, frames_n=64, reps=3):
             "frac_of_hbm_peak": round(byts / ms_tok / 1e6 / peaks["hbm_gbs"], 4)}
 
 
+def batched_decode_block(model, peaks, ids_h, pixels_d, slots=8):
+    """Serving follow-up: `slots` copies of the headline request decoded together with
+    continuous batching over one shared paged pool (vila_b200/serving.py): aggregate tok/s; the weights
+    are streamed once per step for all slots."""
+    import torch
+
+    from vila_b200.serving import BatchedDecoder
+    lc = model.config.llm_cfg
+    emb, _, _ = model._embed(ids_h, {"image": [pixels_d]}, {"image": {}}, None, None)
+    prompt = emb[0].clone()
+    S = prompt.shape[0]
+    dec = BatchedDecoder(model.llm, slots=slots, max_tokens_per_slot=1024, max_new=NEW_TOKENS)
+    dec.capture()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    times = []
+    for rep in range(3):
+        for s_ in range(slots):
+            dec.admit(s_, prompt)
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        dec.run(NEW_TOKENS - 1)
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+        first = [dec.generated(s_)[:4] for s_ in range(slots)]
+        for s_ in range(slots):
+            dec.release(s_)
+    ms = sum(times[1:]) / len(times[1:])
+    step_ms = ms / (NEW_TOKENS - 1)
+    kv = 2 * 2 * (S + NEW_TOKENS // 2) * lc.num_key_value_heads * lc.head_dim * lc.num_hidden_layers * slots
+    byts = llm_weight_bytes(lc) + kv
+    del dec
+    return {"workload": "%d concurrent copies of the headline request (S=%d, %d greedy tokens each), continuous "
+                        "batching over one shared paged pool" % (slots, S, NEW_TOKENS),
+            "slots": slots, "aggregate_tok_s": round(slots * (NEW_TOKENS - 1) / (ms / 1e3), 1),
+            "ms_per_step": round(step_ms, 4), "per_request_tok_s": round(1e3 / step_ms, 1),
+            "bytes_per_step": int(byts), "achieved_gbs": round(byts / step_ms / 1e6, 1),
+            "frac_of_hbm_peak": round(byts / step_ms / 1e6 / peaks["hbm_gbs"], 4),
+            "all_slots_agree": bool(all(f == first[0] for f in first))}
+
+
 def sp_prefill_block(model, args, peaks, rank, world, local):
     """BASELINE configs[4] through the public API with sequence parallelism over this launch's ranks."""
     import torch
@@ -425,6 +469,14 @@ def run_ours(args):
             video = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
             torch.cuda.synchronize()
 
+    batched = None
+    if not (args.profile or args.no_video):
+        try:
+            batched = batched_decode_block(model, peaks, ids_h, pixels_d)
+        except Exception as e:
+            batched = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            torch.cuda.synchronize()
+
     step_ms = [a + b for a, b in zip(ttfts, decs)]
     local_stats = torch.tensor([sum(step_ms) / len(step_ms), sum(decs) / len(decs), sum(ttfts) / len(ttfts),
                                 sum(e2e_full) / len(e2e_full), sum(e2e_first) / len(e2e_first)],
@@ -518,6 +570,7 @@ def run_ours(args):
                           "frac_vision": round(floor_vis / vis_avg, 4),
                           "frac_llm": round(floor_llm / max(ms_ttft - vis_avg, 1e-6), 4)},
         "video_decode": video,
+        "batched_decode": batched,
         "sp_prefill": sp_block,
         "cpu_baseline": cpu,
         "wall_s_timed_region": round(t_wall, 3),

@@ -219,6 +219,13 @@ typedef struct vila_decode_attn_params {
 } vila_decode_attn_params;
 int vila_decode_attention(const vila_decode_attn_params* p, void* stream);
 
+/* Batched decode attention for continuous batching over ONE shared paged pool: `batch` sequences, sequence
+ * b uses qkv + b*qkv_stride, out + b*out_stride, position[b] (< 0: idle slot, skipped) and the page-table
+ * row page_table + b*pt_stride (max_pages <= 32 valid entries: contexts up to 4096 tokens).  ws / counters /
+ * num_splits of the struct are ignored.  One CTA per (query head, sequence); RoPE + KV append fused. */
+int vila_decode_attention_batch(const vila_decode_attn_params* p, int batch, int qkv_stride,
+                                int out_stride, int pt_stride, int max_pages, void* stream);
+
 /* Long-context decode attention (video: 16K-66K cached tokens = 34-135 MB of K/V per layer): RoPE +
  * KV append for the new token, then the tcgen05 FMHA kernel in split-KV mode (the G query heads of a
  * KV group are the query rows of its 128-row tile; K/V pages stream through TMA on

@@ -104,6 +104,7 @@ SIGNATURES = {
     "vila_argmax_finalize": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_void_p],
     "vila_decode_attention": [C.POINTER(DecodeAttnParams), c_void_p],
+    "vila_decode_attention_batch": [C.POINTER(DecodeAttnParams), c_int, c_int, c_int, c_int, c_int, c_void_p],
     "vila_decode_attention_split": [C.POINTER(DecodeAttnSplitParams), c_void_p],
     "vila_decode_mega": [C.POINTER(MegaParams), c_void_p],
 }

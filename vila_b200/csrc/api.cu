@@ -266,6 +266,24 @@ int vila_decode_attention(const vila_decode_attn_params* p, void* stream) {
   return vb::decode_attention(d, st(stream));
 }
 
+int vila_decode_attention_batch(const vila_decode_attn_params* p, int batch, int qkv_stride,
+                                int out_stride, int pt_stride, int max_pages, void* stream) {
+  VB_REQUIRE_DEVICE();
+  vb::DecodeAttnParams d;
+  d.qkv = mb(p->qkv);
+  d.position = p->position;
+  d.k_pool = mb(p->k_pool);
+  d.v_pool = mb(p->v_pool);
+  d.page_table = p->page_table;
+  d.out = mb(p->out);
+  d.ws = nullptr;
+  d.counters = nullptr;
+  d.inv_freq = p->inv_freq;
+  d.Hq = p->Hq; d.Hkv = p->Hkv; d.D = p->D; d.num_splits = 0;
+  d.scale = p->scale;
+  return vb::decode_attention_batch(d, batch, qkv_stride, out_stride, pt_stride, max_pages, st(stream));
+}
+
 int vila_decode_attention_split(const vila_decode_attn_split_params* p, void* stream) {
   VB_REQUIRE_DEVICE();
   vb::DecodeAttnSplitParams d;

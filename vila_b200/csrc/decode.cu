@@ -505,13 +505,31 @@ decode_attn_kernel(DecodeAttnParams p) {
 // Same arithmetic as decode_attn_kernel (RoPE rounding points, bf16 probabilities, fp32 combine).
 // ------------------------------------------------------------------------------------------------
 constexpr int kDhThreads = 256;
-constexpr int kDhMaxPages = 8;  // <= 1024 tokens
+constexpr int kDhMaxPages = 32;  // <= 4096 tokens per sequence
+
+// Batched form (continuous batching over ONE shared paged pool, vila_b200/serving.py): blockIdx.y is
+// the sequence; each has its own row of qkv / out, its own position and its own page-table row.
+// positions[b] < 0 marks an idle slot (the CTA exits).  The single-sequence entry point is batch 1.
+struct DecodeAttnBatchArgs {
+  DecodeAttnParams p;  // qkv / out / position / page_table point at sequence 0
+  int batch;
+  int qkv_stride, out_stride, pt_stride;  // elements between consecutive sequences
+  int max_pages;                          // valid entries per page-table row (<= kDhMaxPages)
+};
 
 template <int D, int TB>
 __global__ void __launch_bounds__(kDhThreads)
-decode_attn_head_kernel(DecodeAttnParams p) {
+decode_attn_head_kernel(DecodeAttnBatchArgs args) {
   static_assert(D == 128, "head_dim 128");
   constexpr int VPT = 8, LPT = D / VPT;
+  DecodeAttnParams p = args.p;
+  {
+    const int b = blockIdx.y;
+    p.qkv += static_cast<size_t>(b) * args.qkv_stride;
+    p.out += static_cast<size_t>(b) * args.out_stride;
+    p.position += b;
+    p.page_table += static_cast<size_t>(b) * args.pt_stride;
+  }
   const int h = blockIdx.x;
   const int ratio = p.Hq / p.Hkv;
   const int hk = h / ratio;
@@ -526,10 +544,11 @@ decode_attn_head_kernel(DecodeAttnParams p) {
   __shared__ float red_m[16], red_l[16];
   __shared__ float red_o[16][D];
 
-  if (threadIdx.x < kDhMaxPages) pages_s[threadIdx.x] = p.page_table[threadIdx.x];  // static: before the wait
+  if (threadIdx.x < args.max_pages) pages_s[threadIdx.x] = p.page_table[threadIdx.x];  // static: before the wait
   griddep_launch_dependents();
   griddep_wait();
   const int pos = *p.position;
+  if (pos < 0) return;  // idle slot (block-uniform)
   const int n_tok = pos + 1;
   __syncthreads();
 
@@ -727,7 +746,8 @@ int decode_attention(const DecodeAttnParams& p, cudaStream_t stream) {
            p.num_splits);
   if (p.num_splits == 0) {
     // one CTA per query head, no split: contexts of at most 1024 tokens (8 pages), see the kernel
-    VB_CUDA(launch_pdl(decode_attn_head_kernel<128, 4>, dim3(p.Hq), dim3(kDhThreads), 0, stream, p));
+    DecodeAttnBatchArgs a{p, 1, 0, 0, 0, 8};
+    VB_CUDA(launch_pdl(decode_attn_head_kernel<128, 4>, dim3(p.Hq), dim3(kDhThreads), 0, stream, a));
     return 0;
   }
   const int G = p.Hq / p.Hkv;
@@ -803,6 +823,19 @@ int decode_attention_split(const DecodeAttnSplitParams& p, cudaStream_t stream) 
   VB_CUDA(launch_pdl(decode_combine_kernel, dim3(p.Hq), dim3(128), 0, stream,
                      static_cast<const float*>(p.o_partial), static_cast<const float*>(p.lse), p.out,
                      p.Hq, p.D, p.num_splits));
+  return 0;
+}
+
+
+int decode_attention_batch(const DecodeAttnParams& p, int batch, int qkv_stride, int out_stride,
+                           int pt_stride, int max_pages, cudaStream_t stream) {
+  VB_CHECK(p.D == 128, "decode_attention_batch: head_dim must be 128 (got %d)", p.D);
+  VB_CHECK(p.Hq % p.Hkv == 0, "decode_attention_batch: Hq %% Hkv != 0");
+  VB_CHECK(batch >= 1 && batch <= 65535, "decode_attention_batch: bad batch %d", batch);
+  VB_CHECK(max_pages >= 1 && max_pages <= kDhMaxPages && max_pages <= pt_stride,
+           "decode_attention_batch: 1 <= max_pages (%d) <= min(%d, pt_stride %d)", max_pages, kDhMaxPages, pt_stride);
+  DecodeAttnBatchArgs a{p, batch, qkv_stride, out_stride, pt_stride, max_pages};
+  VB_CUDA(launch_pdl(decode_attn_head_kernel<128, 4>, dim3(p.Hq, batch), dim3(kDhThreads), 0, stream, a));
   return 0;
 }
 

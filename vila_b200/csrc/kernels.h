@@ -157,6 +157,11 @@ struct DecodeAttnParams {
   float scale;
 };
 int decode_attention(const DecodeAttnParams& p, cudaStream_t stream);
+// batch of sequences over ONE shared paged pool (continuous batching): sequence b uses qkv + b*qkv_stride,
+// out + b*out_stride, position[b] (< 0: idle slot) and page_table + b*pt_stride (max_pages valid entries,
+// <= 32 = 4096 tokens); one CTA per (query head, sequence)
+int decode_attention_batch(const DecodeAttnParams& p, int batch, int qkv_stride, int out_stride,
+                           int pt_stride, int max_pages, cudaStream_t stream);
 struct DecodeAttnSplitParams {
   __nv_bfloat16* qkv;          // [(Hq+2Hkv)*D] pre-RoPE, current token (q / k rotated in place)
   const int32_t* position;     // device scalar: position id of the current token == tokens cached so far

@@ -574,6 +574,24 @@ class LlavaLlamaModel(nn.Module):
         return self.llm.generate(inputs_embeds=inputs_embeds, attention_mask=attention_mask,
                                  sp_runner=self._sp_runner(), **generation_kwargs)
 
+    @torch.inference_mode()
+    def generate_batch(self, requests: List[Dict[str, Any]], max_new_tokens: int = 128, slots: int = 8,
+                       max_tokens_per_slot: int = 2048, eos_token_id=None) -> List[List[int]]:
+        """Serve several independent requests with continuous batching over one shared paged KV pool
+        (vila_b200/serving.py; the reference's servers run them one at a time, serving/server.py:65-73).
+        requests: dicts with the `generate` arguments (`input_ids` [1, T], `media`, `media_config`).
+        Greedy decoding; returns the new ids of every request in order."""
+        from ..serving import generate_batch
+        prompts = []
+        for r in requests:
+            emb, _, mask = self._embed(r["input_ids"], r.get("media"), r.get("media_config"), None,
+                                       r.get("attention_mask"))
+            prompts.append(emb[0][mask[0]] if mask is not None else emb[0])
+        eos = self.tokenizer.stop_token_ids if eos_token_id is None else (
+            [eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id))
+        return generate_batch(self.llm, prompts, max_new_tokens, eos, slots=slots,
+                              max_tokens_per_slot=max_tokens_per_slot)
+
     @property
     def default_generation_config(self):
         """llava_arch.py:950-963 (GenerationConfig fields as a plain namespace)."""

@@ -368,3 +368,23 @@ def decode_attention_split(qkv: torch.Tensor, position: torch.Tensor, k_pool: to
     p.o_partial, p.lse, p.inv_freq = _p(o_partial), _p(lse), _p(inv_freq)
     p.Hq, p.Hkv, p.D, p.num_splits, p.split_tokens, p.scale = Hq, Hkv, D, num_splits, split_tokens, scale
     check(_lib.load().vila_decode_attention_split(C.byref(p), _stream()), "vila_decode_attention_split")
+
+
+def decode_attention_batch(qkv: torch.Tensor, positions: torch.Tensor, k_pool: torch.Tensor,
+                           v_pool: torch.Tensor, page_tables: torch.Tensor, out: torch.Tensor,
+                           inv_freq: torch.Tensor, Hq: int, Hkv: int, D: int, scale: float) -> None:
+    """qkv [B, (Hq+2Hkv)*D], positions int32 [B] (< 0: idle slot), page_tables int32 [B, max_pages],
+    out [B, Hq*D]; one shared paged pool [P, 128, Hkv, D]."""
+    _chk(qkv, "qkv"); _chk(out, "out")
+    B = qkv.shape[0]
+    assert qkv.dim() == 2 and out.shape == (B, Hq * D) and qkv.stride(1) == 1 and out.stride(1) == 1
+    assert positions.dtype == torch.int32 and positions.numel() == B and positions.is_contiguous()
+    assert page_tables.dtype == torch.int32 and page_tables.dim() == 2 and page_tables.shape[0] == B
+    p = DecodeAttnParams()
+    p.qkv, p.position, p.k_pool, p.v_pool = _p(qkv), _p(positions), _p(k_pool), _p(v_pool)
+    p.page_table, p.out, p.ws, p.counters = _p(page_tables), _p(out), None, None
+    p.inv_freq = _p(inv_freq)
+    p.Hq, p.Hkv, p.D, p.num_splits, p.scale = Hq, Hkv, D, 0, scale
+    check(_lib.load().vila_decode_attention_batch(C.byref(p), B, qkv.stride(0), out.stride(0),
+                                                  page_tables.stride(0), min(32, page_tables.shape[1]),
+                                                  _stream()), "vila_decode_attention_batch")
