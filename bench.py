@@ -460,6 +460,28 @@ def run_ours(args):
             e2e_first.append(t1)
     clock_summary = clocks.summary()
     peaks = read_peaks()
+    # TTFT anatomy (outside the timed region): each stage alone, 10 repetitions, CUDA events around
+    # the host call (so host-side Python that is not hidden behind GPU work shows up)
+    def stage(fn, reps=10):
+        fn(); torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    emb0, _, _ = model._embed(ids_h, {"image": [pixels_d]}, media_cfg, None, None)
+    emb0 = emb0[0].clone()
+    dec0 = llm.decoder(NEW_TOKENS)
+    cache0 = dec0.cache_for(emb0.shape[0] + NEW_TOKENS)
+    def _prefill():
+        cache0.length = 0
+        return llm.prefill_hidden_graphed(emb0, cache0)
+    hid0 = _prefill()
+    anatomy = {"encode_images_graph": round(stage(lambda: model.encode_images(pixels_d[None])), 3),
+               "embed_total (encoders + host index table + splice)": round(stage(lambda: model._embed(ids_h, {"image": [pixels_d]}, media_cfg, None, None)), 3),
+               "prefill_graph": round(stage(_prefill), 3),
+               "first_token (lm_head GEMV + finalize)": round(stage(lambda: dec0.start(hid0[-1], cache0)), 3)}
     ledger = decode_kernel_ledger(model, peaks, ctx=S)
     video = None
     if not (args.profile or args.no_video):
@@ -529,6 +551,7 @@ def run_ours(args):
         "ttft_ms": round(ms_ttft, 3), "decode_ms_per_token": round(ms_dec / (NEW_TOKENS - 1), 4),
         "ttft_breakdown_ms": {"vision_projector_splice": round(vis_avg, 3),
                               "llm_prefill_first_token": round(ms_ttft - vis_avg, 3)},
+        "ttft_anatomy_ms": anatomy,
         "config": {"workload": "NVILA-8B bf16, 1x448^2 image, prefill S=%d + %d-token greedy decode, bs=1 "
                                "(BASELINE.json configs[1])" % (S, NEW_TOKENS),
                    "vision": "SigLIP-so400m/14-448 (26 of 27 layers evaluated: hidden_states[-2])",
