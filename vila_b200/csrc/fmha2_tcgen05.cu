@@ -324,14 +324,16 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           const float alpha = ex2f(m_ref - m_new);  // 1 for rows that keep their reference
           mbar_wait(&o_full[t], (j - 1) & 1);       // PV(j-1) has landed in TMEM
           tc_fence_after();
+          // rare path (a row maximum moved by more than 2^8): 8 columns at a time so that it adds no
+          // register pressure to the hot loop, which holds the whole score row
 #pragma unroll 1
-          for (int c = 0; c < DP / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(o_addr + c * 32, r);
+          for (int c = 0; c < DP / 8; ++c) {
+            uint32_t o8[8];
+            tmem_ld_32x32b_x8(o_addr + c * 8, o8);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_32x32b_x32(o_addr + c * 32, r);
+            for (int i = 0; i < 8; ++i) o8[i] = __float_as_uint(__uint_as_float(o8[i]) * alpha);
+            tmem_st_32x32b_x8(o_addr + c * 8, o8);
           }
           tmem_st_wait();
           l *= alpha;
@@ -342,22 +344,24 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_wait(&p_free[t], (j & 1) ^ 1);
       float rowsum = 0.f, rowsum1 = 0.f, rs2 = 0.f, rs3 = 0.f;  // 4 independent accumulation chains
       const float neg_m = -m_ref;
+      // 8 columns at a time: exponentials -> bf16 -> one 16-byte store (keeps the live set small: the
+      // 128 score registers + 8 temporaries; a 32-wide temporary array spilled to local memory)
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        float p[32];
+      for (int g8 = 0; g8 < BKV / 8; ++g8) {
+        float p[8];
         if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float arg = __uint_as_float(r[c * 32 + i]) * a.scale_log2 - m_ref;
-            const float e = (kv0 + c * 32 + i <= kv_lim) ? ex2f(arg) : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            const float arg = __uint_as_float(r[g8 * 8 + i]) * a.scale_log2 - m_ref;
+            const float e = (kv0 + g8 * 8 + i <= kv_lim) ? ex2f(arg) : 0.f;
             p[i] = e;
             rowsum += e;
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
+          for (int i = 0; i < 8; i += 2) {
             float a0, a1;
-            ffma2(a0, a1, __uint_as_float(r[c * 32 + i]), __uint_as_float(r[c * 32 + i + 1]), a.scale_log2, neg_m);
+            ffma2(a0, a1, __uint_as_float(r[g8 * 8 + i]), __uint_as_float(r[g8 * 8 + i + 1]), a.scale_log2, neg_m);
             constexpr int kP = kPolyEvery > 0 ? kPolyEvery : 1;
             p[i] = (kPolyEvery > 0 && (i % kP) == kP - 1) ? ex2_poly(a0) : ex2f(a0);
             p[i + 1] = (kPolyEvery > 0 && ((i + 1) % kP) == kP - 1) ? ex2_poly(a1) : ex2f(a1);
@@ -365,17 +369,14 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             else fadd2(rs2, rs3, p[i], p[i + 1]);
           }
         }
-        uint8_t* prow = my_p + (c >> 1) * (BQ * 128) + row * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int piece = (c & 1) * 4 + g;
-          uint4 v4;
-          v4.x = pack_bf16(p[g * 8 + 0], p[g * 8 + 1]);
-          v4.y = pack_bf16(p[g * 8 + 2], p[g * 8 + 3]);
-          v4.z = pack_bf16(p[g * 8 + 4], p[g * 8 + 5]);
-          v4.w = pack_bf16(p[g * 8 + 6], p[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(prow + ((piece ^ (row & 7)) << 4)) = v4;
-        }
+        // P layout: two [128 rows][64 cols] SW128 chunks; 16-byte piece (g8 & 7) of chunk (g8 >> 3)
+        uint8_t* prow = my_p + (g8 >> 3) * (BQ * 128) + row * 128;
+        uint4 v4;
+        v4.x = pack_bf16(p[0], p[1]);
+        v4.y = pack_bf16(p[2], p[3]);
+        v4.z = pack_bf16(p[4], p[5]);
+        v4.w = pack_bf16(p[6], p[7]);
+        *reinterpret_cast<uint4*>(prow + (((g8 & 7) ^ (row & 7)) << 4)) = v4;
       }
       rowsum += rowsum1 + (rs2 + rs3);
       l += rowsum;
