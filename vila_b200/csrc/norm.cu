@@ -199,7 +199,7 @@ layernorm_warp_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
 }
 
 template <int VPL>
-__global__ void __launch_bounds__(kWarpRowThreads, 2)
+__global__ void __launch_bounds__(kWarpRowThreads, 4)
 rmsnorm_warp_kernel(__nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res_add,
                     const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int rows,
                     int cols, float eps) {
@@ -285,8 +285,11 @@ int rmsnorm_bf16(__nv_bfloat16* x_inout, const __nv_bfloat16* residual_add,
   VB_CHECK(cols % 8 == 0, "rmsnorm: cols must be a multiple of 8 (got %d)", cols);
   VB_CHECK(cols * 2 <= 96 * 1024, "rmsnorm: row too long (%d)", cols);
   if (rows == 0) return 0;
-  if (rows >= kWarpRowMinRows && cols <= 16 * 256) {
-    VB_CUDA(launch_pdl(rmsnorm_warp_kernel<16>, dim3((rows + 7) / 8), dim3(kWarpRowThreads), 0, stream,
+  // rows of up to 2048 elements only: at 3584 (Qwen2-7B) the 14 vectors per lane cost 128 registers,
+  // i.e. fewer resident warps, and the warp-per-row form measured SLOWER than one CTA per row
+  // (ncu, 16470 x 3584: 84 vs 57 us)
+  if (rows >= kWarpRowMinRows && cols <= 8 * 256) {
+    VB_CUDA(launch_pdl(rmsnorm_warp_kernel<8>, dim3((rows + 7) / 8), dim3(kWarpRowThreads), 0, stream,
                        x_inout, residual_add, w, out, rows, cols, eps));
     return 0;
   }
