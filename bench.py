@@ -326,13 +326,19 @@ def sp_prefill_block(model, args, peaks, rank, world, local):
         return a.elapsed_time(b), int(out[0, 0])
 
     try:
+        est = 0.0
         for _ in range(max(3, args.warmup) if not args.profile else 1):
-            step()
+            est = step()[0]
+        # at least --sp-steps steps, and long enough for >= 20 nvidia-smi clock samples (a query takes
+        # ~0.5 s on an 8-GPU box): ~12 s of timed steps, capped at 64 steps; same count on every rank
+        n_steps = torch.tensor([max(args.sp_steps, min(64, int(12000.0 / max(est, 1.0)) + 1))], device="cuda")
+        dist.all_reduce(n_steps, op=dist.ReduceOp.MAX)
+        n_steps = int(n_steps)
         dist.barrier(); torch.cuda.synchronize()
         vis_events.clear()
         rows = []
         with ClockSampler(local, period=0.1) as clocks:
-            for _ in range(args.sp_steps):
+            for _ in range(n_steps):
                 rows.append(step())
             dist.barrier(); torch.cuda.synchronize()
         tot = torch.tensor([sum(r[0] for r in rows) / len(rows),
@@ -357,7 +363,7 @@ def sp_prefill_block(model, args, peaks, rank, world, local):
     return {"workload": "LongVILA-8B %d frames x 448^2, S=%d tokens: vision tower sharded by frames + zigzag "
                         "SP-%d prefill + first token (BASELINE.json configs[4])" % (F, S, world),
             "api": "vila_b200.sp.set_sequence_parallel_group(); LlavaLlamaModel.generate(media={'video': [...]}, max_new_tokens=1)",
-            "scaling": "strong", "n_gpus": world, "steps": args.sp_steps, "warmup": max(3, args.warmup),
+            "scaling": "strong", "n_gpus": world, "steps": n_steps, "warmup": max(3, args.warmup),
             "ms_per_step": round(ms, 2), "tok_s": round(S / (ms / 1e3), 1),
             "phase_ms_max_over_ranks": {"vision_tower_projector_gather": round(vis_ms, 2),
                                         "splice_sp_prefill_first_token": round(ms - vis_ms, 2)},

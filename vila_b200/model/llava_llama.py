@@ -445,48 +445,56 @@ class LlavaLlamaModel(nn.Module):
         media_rows: List[torch.Tensor] = []
         media_off = 0
         srcs, labs = [], []
+        media_id_list = torch.tensor(sorted(tok2name), dtype=ids_host.dtype)
         for k in range(bsz):
-            ids_k = ids_host[k].tolist()
-            lab_k = labels_host[k][mask_host[k]].tolist()
-            n_valid = len(lab_k)
             # NOTE (reference quirk kept): positions index the UNMASKED input_ids (llava_arch.py:463)
-            src_k: List[int] = []
-            out_lab: List[int] = []
-            text_ids = ids_host[k][mask_host[k]].tolist()
-            pos = 0
-            while pos < n_valid:
-                if ids_k[pos] in tok2name:
-                    emb = media_embeds[tok2name[ids_k[pos]]].popleft()
-                    n = emb.shape[0]
-                    media_rows.append(emb)
-                    src_k.extend(range(-(media_off + 1), -(media_off + n + 1), -1))
-                    out_lab.extend([IGNORE_INDEX] * n)
-                    media_off += n
-                else:
-                    src_k.append(text_ids[pos])
-                    out_lab.append(lab_k[pos])
-                pos += 1
-            srcs.append(src_k)
-            labs.append(out_lab)
+            # while the text embeddings / labels come from the masked rows (:447)
+            text_ids = ids_host[k][mask_host[k]]
+            lab_k = labels_host[k][mask_host[k]]
+            n_valid = lab_k.shape[0]
+            ids_k = ids_host[k][:n_valid]
+            # the index table is assembled from tensor segments (text runs / one arange per media
+            # item): a 256-frame video is ONE segment of 65.8K rows, not 65.8K Python ints
+            src_parts: List[torch.Tensor] = []
+            lab_parts: List[torch.Tensor] = []
+            prev = 0
+            for pos in torch.nonzero(torch.isin(ids_k, media_id_list)).flatten().tolist():
+                if pos > prev:
+                    src_parts.append(text_ids[prev:pos].to(torch.int32))
+                    lab_parts.append(lab_k[prev:pos])
+                emb = media_embeds[tok2name[int(ids_k[pos])]].popleft()
+                n = emb.shape[0]
+                media_rows.append(emb)
+                src_parts.append(-torch.arange(media_off + 1, media_off + n + 1, dtype=torch.int32))
+                lab_parts.append(torch.full((n,), IGNORE_INDEX, dtype=lab_k.dtype))
+                media_off += n
+                prev = pos + 1
+            if n_valid > prev:
+                src_parts.append(text_ids[prev:n_valid].to(torch.int32))
+                lab_parts.append(lab_k[prev:n_valid])
+            srcs.append(torch.cat(src_parts) if src_parts else torch.zeros(0, dtype=torch.int32))
+            labs.append(torch.cat(lab_parts) if lab_parts else torch.zeros(0, dtype=lab_k.dtype))
         for name in media_embeds:
             if media_embeds[name]:
                 raise ValueError(f"Not all {name} embeddings are consumed!")
 
         # __truncate_sequence applies only in training (llava_arch.py:519-526); __batchify_sequence :528-555
-        max_len = max(len(s) for s in srcs)
+        max_len = max(int(s.shape[0]) for s in srcs)
         hidden = self.config.hidden_size
         right = self.tokenizer.padding_side == "right"
         src_all = torch.zeros((bsz, max_len), dtype=torch.int32)
         lab_all = torch.full((bsz, max_len), IGNORE_INDEX, dtype=labels_host.dtype)
         mask_all = torch.zeros((bsz, max_len), dtype=torch.bool)
         for k in range(bsz):
-            n = len(srcs[k])
+            n = int(srcs[k].shape[0])
             sl = slice(0, n) if right else slice(max_len - n, max_len)
-            src_all[k, sl] = torch.tensor(srcs[k], dtype=torch.int32)
-            lab_all[k, sl] = torch.tensor(labs[k], dtype=labels_host.dtype)
+            src_all[k, sl] = srcs[k]
+            lab_all[k, sl] = labs[k]
             mask_all[k, sl] = True
         dev = self.device
-        media_buf = torch.cat(media_rows, dim=0).contiguous() if media_rows else None
+        media_buf = None
+        if media_rows:  # one media item (a long video): no 0.5 GB copy
+            media_buf = media_rows[0].contiguous() if len(media_rows) == 1 else torch.cat(media_rows, dim=0)
         embeds = ops.embed_splice(self.llm.model.embed_tokens.weight, media_buf,
                                   src_all.view(-1).to(dev, non_blocking=True))
         embeds = embeds.view(bsz, max_len, hidden)
