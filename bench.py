@@ -315,6 +315,19 @@ def sp_prefill_block(model, args, peaks, rank, world, local):
         return r
 
     model._encode_frames = timed_encode
+    runner = model._sp_runner()
+    pre_events = []
+    orig_prefill = runner.prefill_hidden
+
+    def timed_prefill(*a, **k):
+        e0, e1 = ev(), ev()
+        e0.record()
+        r = orig_prefill(*a, **k)
+        e1.record()
+        pre_events.append((e0, e1))
+        return r
+
+    runner.prefill_hidden = timed_prefill
 
     def step():
         a, b = ev(), ev()
@@ -336,16 +349,18 @@ def sp_prefill_block(model, args, peaks, rank, world, local):
         n_steps = int(n_steps)
         dist.barrier(); torch.cuda.synchronize()
         vis_events.clear()
+        pre_events.clear()
         rows = []
         with ClockSampler(local, period=0.1) as clocks:
             for _ in range(n_steps):
                 rows.append(step())
             dist.barrier(); torch.cuda.synchronize()
         tot = torch.tensor([sum(r[0] for r in rows) / len(rows),
-                            sum(a.elapsed_time(b) for a, b in vis_events) / max(1, len(vis_events))],
+                            sum(a.elapsed_time(b) for a, b in vis_events) / max(1, len(vis_events)),
+                            sum(a.elapsed_time(b) for a, b in pre_events) / max(1, len(pre_events))],
                            device="cuda", dtype=torch.float64)
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-        ms, vis_ms = float(tot[0]), float(tot[1])
+        ms, vis_ms, pre_ms = float(tot[0]), float(tot[1]), float(tot[2])
         tok = rows[-1][1]
         toks = torch.tensor([tok], device="cuda")
         all_toks = [torch.zeros_like(toks) for _ in range(world)]
@@ -354,6 +369,7 @@ def sp_prefill_block(model, args, peaks, rank, world, local):
         top = torch.topk(logits, 5)
     finally:
         model._encode_frames = orig
+        runner.prefill_hidden = orig_prefill
         sp.set_sequence_parallel_group(None, enabled=False)
     gemm_flops = 2.0 * 6.525e9 * S
     attn_flops = 2.0 * S * S * lc.num_attention_heads * lc.head_dim * lc.num_hidden_layers
@@ -366,7 +382,8 @@ def sp_prefill_block(model, args, peaks, rank, world, local):
             "scaling": "strong", "n_gpus": world, "steps": n_steps, "warmup": max(3, args.warmup),
             "ms_per_step": round(ms, 2), "tok_s": round(S / (ms / 1e3), 1),
             "phase_ms_max_over_ranks": {"vision_tower_projector_gather": round(vis_ms, 2),
-                                        "splice_sp_prefill_first_token": round(ms - vis_ms, 2)},
+                                        "sp_prefill_28_layers": round(pre_ms, 2),
+                                        "splice_host_glue_first_token": round(ms - vis_ms - pre_ms, 2)},
             "padded_len": plan.padded_len, "chunk": plan.chunk,
             "first_token_id": tok, "first_token_ids_all_ranks": [int(t) for t in all_toks],
             "logits_top5_ids": [int(i) for i in top.indices], "logits_top5": [round(float(v), 4) for v in top.values],

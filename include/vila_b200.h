@@ -243,6 +243,8 @@ typedef struct vila_decode_attn_split_params {
   void* out;
   float* o_partial; /* >= num_splits*Hq*D floats */
   float* lse;       /* >= num_splits*Hq floats */
+  int32_t* counters; /* Hkv ints, zero before the first launch (self-cleaning): the last split CTA of a KV head
+                        merges the partials itself; NULL: a separate combine kernel is launched */
   const float* inv_freq;
   int32_t Hq, Hkv, D, num_splits, split_tokens;
   float scale;

@@ -662,6 +662,14 @@ def test_decode_attention_split_long_context(cuda, ctx, splits, split_tokens):
     qkv = qkv0.clone()
     ops.decode_attention_split(qkv, pos, k_pool, v_pool, perm, out, o_partial, lse, inv, Hq, Hkv, D, splits,
                                split_tokens, D ** -0.5)
+    # fused combine (last split CTA of a KV head merges): same result bit for bit, counters re-armed
+    out_f = torch.zeros_like(out)
+    cnt_f = torch.zeros(Hkv, dtype=torch.int32, device=cuda)
+    for _ in range(2):
+        kp2, vp2 = k_pool.clone(), v_pool.clone()
+        ops.decode_attention_split(qkv0.clone(), pos, kp2, vp2, perm, out_f, o_partial, lse, inv, Hq, Hkv, D,
+                                   splits, split_tokens, D ** -0.5, counters=cnt_f)
+        assert torch.equal(out_f, out) and int(cnt_f.abs().sum()) == 0
     q = qkv0[:Hq * D].view(1, Hq, D).transpose(0, 1)
     kn = qkv0[Hq * D:(Hq + Hkv) * D].view(1, Hkv, D).transpose(0, 1)
     vn = qkv0[(Hq + Hkv) * D:].view(1, Hkv, D)

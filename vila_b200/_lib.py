@@ -50,7 +50,7 @@ class DecodeAttnSplitParams(C.Structure):
     _fields_ = [
         ("qkv", c_void_p), ("position", c_void_p), ("k_pool", c_void_p), ("v_pool", c_void_p),
         ("page_table", c_void_p), ("kv_num_pages", c_i64), ("out", c_void_p), ("o_partial", c_void_p),
-        ("lse", c_void_p), ("inv_freq", c_void_p),
+        ("lse", c_void_p), ("counters", c_void_p), ("inv_freq", c_void_p),
         ("Hq", C.c_int32), ("Hkv", C.c_int32), ("D", C.c_int32), ("num_splits", C.c_int32),
         ("split_tokens", C.c_int32), ("scale", c_float),
     ]

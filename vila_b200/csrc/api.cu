@@ -296,6 +296,7 @@ int vila_decode_attention_split(const vila_decode_attn_split_params* p, void* st
   d.out = mb(p->out);
   d.o_partial = p->o_partial;
   d.lse = p->lse;
+  d.counters = p->counters;
   d.inv_freq = p->inv_freq;
   d.Hq = p->Hq; d.Hkv = p->Hkv; d.D = p->D; d.num_splits = p->num_splits; d.split_tokens = p->split_tokens;
   d.scale = p->scale;

@@ -780,12 +780,14 @@ int decode_attention(const DecodeAttnParams& p, cudaStream_t stream) {
 }
 
 
-// Long-context decode attention in three launches (all PDL, graph-capturable, position on the device):
+// Long-context decode attention in two launches (three without `counters`; all PDL, graph-capturable,
+// position on the device):
 //   1. rope_kv_append on the one new token: RoPE(q, k_new) in place, k/v appended at slot = position
 //   2. fmha_decode_split: the tcgen05 FMHA kernel with the G query heads of a KV group as its query
 //      rows and the KV splits as blockIdx.z: K/V pages stream through TMA into the warp-specialised
 //      producer / MMA / softmax pipeline on every SM
-//   3. decode_combine_kernel
+//   3. the combine: by the last split CTA of every KV head inside (2) when `counters` is given, else
+//      decode_combine_kernel
 int decode_attention_split(const DecodeAttnSplitParams& p, cudaStream_t stream) {
   VB_CHECK(p.D == 128, "decode_attention_split: head_dim must be 128 (got %d)", p.D);
   VB_CHECK(p.Hq % p.Hkv == 0, "decode_attention_split: Hq %% Hkv != 0");
@@ -807,7 +809,7 @@ int decode_attention_split(const DecodeAttnSplitParams& p, cudaStream_t stream) 
   f.kv_num_pages = p.kv_num_pages;
   f.page_table = p.page_table;
   f.page_table_stride = 0;
-  f.o = nullptr;
+  f.o = p.counters ? p.out : nullptr;   // fused combine writes out[(hk*G + g)*D + d]
   f.o_tok_stride = p.D;
   f.o_head_stride = static_cast<int64_t>(G) * p.D;
   f.B = p.num_splits;
@@ -818,8 +820,9 @@ int decode_attention_split(const DecodeAttnSplitParams& p, cudaStream_t stream) 
   f.D = p.D;
   f.causal = 0;
   f.scale = p.scale;
-  rc = fmha_decode_split(f, p.position, p.split_tokens, p.o_partial, p.lse, stream);
+  rc = fmha_decode_split(f, p.position, p.split_tokens, p.o_partial, p.lse, p.counters, stream);
   if (rc) return rc;
+  if (p.counters != nullptr) return 0;  // combined by the last split CTA of every KV head
   VB_CUDA(launch_pdl(decode_combine_kernel, dim3(p.Hq), dim3(128), 0, stream,
                      static_cast<const float*>(p.o_partial), static_cast<const float*>(p.lse), p.out,
                      p.Hq, p.D, p.num_splits));

@@ -76,6 +76,7 @@ struct FmhaKernelArgs {
   int split_tokens;
   float* o_partial;  // [splits][Hq][Sq][D]
   float* lse_out;    // [splits][Hq][Sq]
+  int* split_counters;  // [Hq] zero-initialised, self-cleaning; non-null: the last CTA of a head combines into o
 };
 
 template <int DP, int CW>
@@ -373,6 +374,40 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                                  o_acc[g * 4 + 3] * inv);
         }
       }
+      if (a.split_counters != nullptr) {
+        // Fused combine: the LAST split CTA of this KV head to finish merges all partials (fixed split
+        // order -> deterministic) and writes the bf16 output, saving the separate combine launch.
+        __shared__ int is_last_s;
+        __threadfence();                                   // this thread's partial row is visible device-wide
+        asm volatile("bar.sync 1, 128;" ::: "memory");    // the four softmax warps
+        if (threadIdx.x == 0) {
+          const int prev = atomicAdd(&a.split_counters[h], 1);
+          is_last_s = (prev == static_cast<int>(gridDim.z) - 1);
+          if (is_last_s) a.split_counters[h] = 0;          // re-arm for the next launch / graph replay
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (is_last_s) {
+          __threadfence();
+          const int nsp = static_cast<int>(gridDim.z);
+          const int d = threadIdx.x;                       // 128 threads <-> D = 128 columns
+          for (int g = 0; g < a.Sq; ++g) {
+            float mx = -INFINITY;
+            for (int s = 0; s < nsp; ++s)
+              mx = fmaxf(mx, __ldcg(&a.lse_out[(static_cast<int64_t>(s) * a.Hq + h) * a.Sq + g]));
+            float den = 0.f, acc = 0.f;
+            for (int s = 0; s < nsp; ++s) {
+              const int64_t r = (static_cast<int64_t>(s) * a.Hq + h) * a.Sq + g;
+              const float v = __ldcg(&a.lse_out[r]);
+              const float w = (v == -INFINITY) ? 0.f : exp2f(v - mx);
+              den += w;
+              acc += w * __ldcg(&a.o_partial[r * a.D + d]);
+            }
+            const float inv_den = den > 0.f ? 1.f / den : 0.f;  // same arithmetic as decode_combine_kernel
+            a.o[static_cast<int64_t>(g) * a.o_tok_stride + static_cast<int64_t>(h) * a.o_head_stride + d] =
+                __float2bfloat16(acc * inv_den);
+          }
+        }
+      }
     } else if (q_idx < a.Sq) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
       __nv_bfloat16* dst = a.o + static_cast<int64_t>(b * a.Sq + q_idx) * a.o_tok_stride +
@@ -404,6 +439,7 @@ struct SplitArgs {
   int split_tokens;
   float* o_partial;
   float* lse_out;
+  int* counters;
 };
 
 template <int DP, int CW>
@@ -448,6 +484,7 @@ int launch_fmha(const FmhaParams& p, cudaStream_t stream, const SplitArgs* split
   a.split_tokens = split ? split->split_tokens : 0;
   a.o_partial = split ? split->o_partial : nullptr;
   a.lse_out = split ? split->lse_out : nullptr;
+  a.split_counters = split ? split->counters : nullptr;
   auto kern = fmha_fwd_kernel<DP, CW>;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
@@ -468,13 +505,14 @@ int fmha_prefill(const FmhaParams& p, cudaStream_t stream) { return fmha_prefill
 // after the dependency wait, so one captured graph serves every decode position), K/V paged.  Writes
 // normalised fp32 partials [B][Hq][Sq][D] and their log2-sum-exp [B][Hq][Sq]; non-causal.
 int fmha_decode_split(const FmhaParams& p, const int32_t* n_tok_minus_1, int split_tokens,
-                      float* o_partial, float* lse, cudaStream_t stream) {
+                      float* o_partial, float* lse, int* counters, cudaStream_t stream) {
   VB_CHECK(p.D == 128, "fmha_decode_split: head dim must be 128");
   VB_CHECK(p.kv_page_stride != 0 && p.page_table != nullptr, "fmha_decode_split: K/V must be paged");
   VB_CHECK(split_tokens > 0 && split_tokens % BKV == 0, "fmha_decode_split: split_tokens %% 128 != 0");
   VB_CHECK(p.Sq >= 1 && p.Sq <= BQ && !p.causal, "fmha_decode_split: 1..128 query rows, non-causal");
   VB_CHECK(n_tok_minus_1 && o_partial && lse, "fmha_decode_split: null output / length pointer");
-  SplitArgs sa{n_tok_minus_1, split_tokens, o_partial, lse};
+  VB_CHECK(counters == nullptr || p.o != nullptr, "fmha_decode_split: fused combine needs the output pointer");
+  SplitArgs sa{n_tok_minus_1, split_tokens, o_partial, lse, counters};
   return launch_fmha<128, 64>(p, stream, &sa);
 }
 

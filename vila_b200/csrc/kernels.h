@@ -69,8 +69,9 @@ int fmha_prefill_cfg(int variant, const FmhaParams& p, cudaStream_t stream);  //
 // poly_every: every n-th exponential on the FMA pipe (0 = none, the default; 4; 2) — test/bench hook
 int fmha_prefill_v2(const FmhaParams& p, cudaStream_t stream, int poly_every = 0);  // -1: shape not handled
 // split-KV mode of the one-tile kernel for decode at long context (see fmha_tcgen05.cu)
+// counters != nullptr ([Hq] ints, zero-initialised once): the last split CTA of a head combines into p.o
 int fmha_decode_split(const FmhaParams& p, const int32_t* n_tok_minus_1, int split_tokens,
-                      float* o_partial, float* lse, cudaStream_t stream);
+                      float* o_partial, float* lse, int* counters, cudaStream_t stream);
 
 // ---- norms ---------------------------------------------------------------------------------------
 int layernorm_bf16(const __nv_bfloat16* x, const __nv_bfloat16* w, const __nv_bfloat16* b,
@@ -172,6 +173,7 @@ struct DecodeAttnSplitParams {
   __nv_bfloat16* out;          // [Hq*D]
   float* o_partial;            // [num_splits, Hq, D] fp32
   float* lse;                  // [num_splits, Hq]
+  int32_t* counters;           // [Hkv] zero-initialised once (self-cleaning), or null: separate combine launch
   const float* inv_freq;
   int Hq, Hkv, D, num_splits, split_tokens;
   float scale;

@@ -565,7 +565,7 @@ class GraphDecoder:
                 ops.decode_attention_split(self.qkv, self.position, cache.k(li), cache.v(li),
                                            cache.page_table, self.attn, self.o_partial, self.lse,
                                            llm.inv_freq, Hq, Hkv, D, self.num_splits, self.split_tokens,
-                                           D ** -0.5)
+                                           D ** -0.5, counters=self.counters)
             else:
                 ops.decode_attention(self.qkv, self.position, cache.k(li), cache.v(li), cache.page_table,
                                      self.attn, self.ws, self.counters, llm.inv_freq, Hq, Hkv, D,

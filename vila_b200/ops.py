@@ -358,14 +358,17 @@ def decode_attention(qkv: torch.Tensor, position: torch.Tensor, k_pool: torch.Te
 def decode_attention_split(qkv: torch.Tensor, position: torch.Tensor, k_pool: torch.Tensor,
                            v_pool: torch.Tensor, page_table: torch.Tensor, out: torch.Tensor,
                            o_partial: torch.Tensor, lse: torch.Tensor, inv_freq: torch.Tensor, Hq: int,
-                           Hkv: int, D: int, num_splits: int, split_tokens: int, scale: float) -> None:
-    """Long-context decode attention: RoPE + KV append, tcgen05 FMHA in split-KV mode, combine."""
+                           Hkv: int, D: int, num_splits: int, split_tokens: int, scale: float,
+                           counters: Optional[torch.Tensor] = None) -> None:
+    """Long-context decode attention: RoPE + KV append, tcgen05 FMHA in split-KV mode, combine
+    (counters int32 [Hkv], zeroed once: the combine is fused into the split kernel)."""
     assert o_partial.dtype == torch.float32 and o_partial.numel() >= num_splits * Hq * D
     assert lse.dtype == torch.float32 and lse.numel() >= num_splits * Hq
     p = DecodeAttnSplitParams()
     p.qkv, p.position, p.k_pool, p.v_pool = _p(qkv), _p(position), _p(k_pool), _p(v_pool)
     p.page_table, p.kv_num_pages, p.out = _p(page_table), k_pool.shape[0], _p(out)
     p.o_partial, p.lse, p.inv_freq = _p(o_partial), _p(lse), _p(inv_freq)
+    p.counters = _p(counters)
     p.Hq, p.Hkv, p.D, p.num_splits, p.split_tokens, p.scale = Hq, Hkv, D, num_splits, split_tokens, scale
     check(_lib.load().vila_decode_attention_split(C.byref(p), _stream()), "vila_decode_attention_split")
 
