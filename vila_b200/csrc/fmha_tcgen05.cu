@@ -377,6 +377,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (a.split_counters != nullptr) {
         // Fused combine: the LAST split CTA of this KV head to finish merges all partials (fixed split
         // order -> deterministic) and writes the bf16 output, saving the separate combine launch.
+        // MEASURED SLOWER than the separate 28-CTA combine kernel (one CTA per KV head walks
+        // G x splits partial rows serially: 54 vs 28.6 us at 16.4K tokens, tools/bench_decode_attn.py);
+        // kept as an option of the entry point, not used by the decoder.
         __shared__ int is_last_s;
         __threadfence();                                   // this thread's partial row is visible device-wide
         asm volatile("bar.sync 1, 128;" ::: "memory");    // the four softmax warps
