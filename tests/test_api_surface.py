@@ -175,3 +175,63 @@ def test_remote_code_generate_prepends_prompt_ids(monkeypatch):
     gc = SimpleNamespace(num_return_sequences=2)
     monkeypatch.setattr(LlavaLlamaModel, "generate", lambda self, **kw: torch.tensor([[7], [8]]))
     assert VILAForCausalLM.generate(m, input_ids=ids, generation_config=gc).tolist() == [[1, 2, 3, 4, 7], [1, 2, 3, 4, 8]]
+
+
+def test_chat_completions_server_plumbing():
+    """f3: the OpenAI-style endpoint (reference serving/server.py:209-300) on a stub model — request
+    schema, prompt assembly from base64 image parts, streaming SSE chunks, and grouping of concurrent
+    non-streaming requests into one generate_batch call."""
+    import asyncio
+    import base64
+    import io
+    from PIL import Image as PILImage
+    from vila_b200 import server as S
+    buf = io.BytesIO()
+    PILImage.fromarray(np.random.RandomState(0).randint(0, 256, (32, 48, 3), dtype=np.uint8)).save(buf, format="PNG")
+    url = "data:image/png;base64," + base64.b64encode(buf.getvalue()).decode()
+    calls = {"batch": [], "single": 0}
+
+    class Tok:
+        def decode(self, ids, skip_special_tokens=True):
+            return " ".join(str(i) for i in ids)
+
+    class Stub:
+        tokenizer = Tok()
+        default_generation_config = SimpleNamespace(max_new_tokens=None)
+
+        def generate_content(self, prompt, generation_config=None, response_format=None, stream=False):
+            assert any(hasattr(p, "size") for p in prompt)  # the PIL image made it into the prompt
+            if stream:
+                return iter(["he", "", "llo"])
+            calls["single"] += 1
+            return "single"
+
+        def _prepare_content(self, prompt):
+            return torch.tensor([[1, 2]]), {"image": [torch.zeros(3, 4, 4)]}, {}
+
+        def generate_batch(self, requests, max_new_tokens=128, slots=8):
+            calls["batch"].append(len(requests))
+            return [[7, 8, 9, 10][:max_new_tokens] for _ in requests]
+
+    def req(stream=False, max_tokens=3):
+        return S.ChatCompletionRequest(model="m", stream=stream, max_tokens=max_tokens, messages=[S.ChatMessage(
+            role="user", content=[S.TextContent(type="text", text="describe"),
+                                  S.ImageContent(type="image_url", image_url=S.MediaURL(url=url))])])
+
+    async def scenario():
+        eng = S.Engine(Stub(), "m", slots=4)
+        one = await eng.complete(req())
+        three = await asyncio.gather(*[eng.complete(req()) for _ in range(3)])
+        chunks = [c async for c in eng.stream(req(stream=True))]
+        return one, three, chunks
+
+    one, three, chunks = asyncio.run(scenario())
+    assert one["object"] == "chat.completion" and one["choices"][0]["message"]["content"] == "single"
+    # the first of three concurrent requests finds the engine idle and runs alone; the two that pile up
+    # behind the lock are decoded together by ONE generate_batch call
+    assert [t["choices"][0]["message"]["content"] for t in three] == ["single", "7 8 9", "7 8 9"]
+    assert calls["batch"] == [2] and calls["single"] == 2
+    assert chunks[-1] == "data: [DONE]\n\n" and len(chunks) == 3
+    assert json.loads(chunks[0][6:])["choices"][0]["delta"]["content"] == "he"
+    with pytest.raises(ValueError):
+        asyncio.run(S.Engine(Stub(), "other").complete(req()))
