@@ -580,11 +580,14 @@ int launch_skinny(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int l
   a.epi = epi;
   a.dbg = nullptr;
   a.dbg_skip = 0;
+#ifdef VILA_B200_DEBUG_HOOKS  // profiling aids, compiled OUT of the shipped library (an env var
+                              // must not be able to make a kernel write through an arbitrary pointer)
   if (const char* e = getenv("VILA_B200_GEMM_DEBUG_SKIP")) a.dbg_skip = atoi(e);
-  if (const char* e = getenv("VILA_B200_GEMM_DEBUG")) {  // profiling aid: hex device pointer
+  if (const char* e = getenv("VILA_B200_GEMM_DEBUG")) {  // hex device pointer (tools/skinny_phase_times.py)
     unsigned long long ptr = 0;
     if (sscanf(e, "%llx", &ptr) == 1) a.dbg = reinterpret_cast<long long*>(ptr);
   }
+#endif
   a.stages = stages;
   CUtensorMap tw, tx;
   if (make_tmap_2d_bf16(&tw, W, N, K, ldw, BW, BK, 128)) return 1;
