@@ -17,6 +17,8 @@ shapes = {
     "mid_vit16_qkv": (16384, 3456, 1152), "mid_vit16_fc2": (16384, 1152, 4304),
     "mid_vit4_fc1": (4096, 4304, 1152), "mid_llm2k_o": (2048, 3584, 3584),
     "mid_llm2k_gu": (2048, 37888, 3584), "mid_llm1k_down": (1280, 3584, 18944),
+    # batched video / SP shapes (banded rasterisation)
+    "vit64_qkv": (65536, 3456, 1152), "vit64_fc1": (65536, 4304, 1152), "sp8_gu": (8448, 37888, 3584),
 }
 if len(sys.argv) > 1:  # optional name filter, e.g. "llm"
     shapes = {k: v for k, v in shapes.items() if any(a in k for a in sys.argv[1:])}

@@ -1,4 +1,4 @@
-"""gpurun_out/bench_gemm.json -> profiles/r01_gemm_configs.md (markdown table)."""
+"""gpurun_out/bench_gemm.json -> profiles/r02_gemm_configs.md (markdown table)."""
 import json, sys
 from pathlib import Path
 d = json.loads(Path(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/bench_gemm.json").read_text())
@@ -12,8 +12,9 @@ shapes = {
     "big": (8192, 8192, 8192), "mid_vit16_qkv": (16384, 3456, 1152), "mid_vit16_fc2": (16384, 1152, 4304),
     "mid_vit4_fc1": (4096, 4304, 1152), "mid_llm2k_o": (2048, 3584, 3584),
     "mid_llm2k_gu": (2048, 37888, 3584), "mid_llm1k_down": (1280, 3584, 18944),
+    "vit64_qkv": (65536, 3456, 1152), "vit64_fc1": (65536, 4304, 1152), "sp8_gu": (8448, 37888, 3584),
 }
-out = ["# r01 — tcgen05 GEMM configurations vs cuBLAS on B200 (tools/bench_gemm.py, CUDA events, us per call,",
+out = ["# r02 — tcgen05 GEMM configurations vs cuBLAS on B200 (tools/bench_gemm.py, CUDA events, us per call,",
        "weights rotated through > L2 worth of copies)", "",
        "`dispatch` = what `vila_linear` picks by itself; the other columns force a kernel through `vila_linear_cfg`.", "",
        "| shape (M,N,K) | cuBLAS | " + " | ".join(names[c] for c in cfgs) + " |",
@@ -31,5 +32,5 @@ for k, row in d.items():
 out += ["", "Reading: CTA pairs (`tcgen05.mma.cta_group::2`, 256x256 tiles) win once they fill the SM pairs (large M);",
         "the swap-AB skinny kernel with cluster split-K wins for M = 279 (weights stream once); split-K CTA pairs",
         "(DSMEM exchange) win for long-K GEMMs with <= 74 tiles (ViT fc2); the single-CTA tiles cover the rest."]
-Path("profiles/r01_gemm_configs.md").write_text("\n".join(out) + "\n")
+Path("profiles/r02_gemm_configs.md").write_text("\n".join(out) + "\n")
 print("\n".join(out))
