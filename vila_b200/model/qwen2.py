@@ -509,12 +509,17 @@ class GraphDecoder:
         self.lse = torch.zeros(self.MAX_SPLITS * Hq, device=dev, dtype=torch.float32)
         self.split_tokens = 0  # > 0: the long-context path is active for the current cache
         self.cache: Optional[PagedKVCache] = None
-        self.graphs = {}  # num_splits -> captured CUDA graph of one decode step (for self.cache)
-        self.launches_per_step = 5 * cfg.num_hidden_layers + 2
+        self.graphs = {}  # (num_splits, split_tokens) -> captured CUDA graph of one decode step (for self.cache)
 
     @property
     def graph(self):
         return self.graphs.get((self.num_splits, self.split_tokens))
+
+    @property
+    def launches_per_step(self) -> int:
+        """kernels of one decode step: 5 per layer (7 on the long-context path: RoPE/append, split-KV
+        attention, combine) + lm_head GEMV + finalize"""
+        return (7 if self.split_tokens else 5) * self.llm.config.num_hidden_layers + 2
 
     LONG_CTX = 1024  # above: tcgen05 split-KV path (16.8 us at 2000 tokens vs 24.4 for the SIMT kernel)
 
@@ -633,7 +638,10 @@ class MegaDecoder(GraphDecoder):
         self.attn_ws = torch.zeros(Hkv * num_splits * (Hq // Hkv) * (D + 2), device=dev, dtype=torch.float32)
         self.layer_table = None
         self._table_key = None
-        self.launches_per_step = 1
+
+    @property
+    def launches_per_step(self) -> int:
+        return 1
 
     def _table(self):
         cache = self.cache
