@@ -185,6 +185,9 @@ qkv_big = rn(Sv, NQ)
 posv = torch.arange(Sv, dtype=torch.int32, device=dev)
 entry("rope_kv_append S=16470", 2 * (2 * Sv * (Hq + Hkv) * D + 2 * Sv * Hkv * D), 0,
       lambda: ops.rope_kv_append(qkv_big, posv, Hq, Hkv, D, inv, kpv, vpv, ptv, 0))
+tbl_big = ops.rope_table(posv, D, inv)
+entry("rope_kv_append_table S=16470 (cos/sin table, 16-byte accesses)", 2 * (2 * Sv * (Hq + Hkv) * D + 2 * Sv * Hkv * D), 0,
+      lambda: ops.rope_kv_append_table(qkv_big, tbl_big, Hq, Hkv, D, kpv, vpv, ptv, 0))
 entry("rmsnorm 16470x3584", 2 * 2 * Sv * Hd, 0, lambda: ops.rmsnorm(xv.clone(), nw, 1e-6))
 entry("layernorm 65536x1152", 2 * 2 * 65536 * C, 0, lambda: ops.layernorm(x64, lnw, lnb, 1e-6))
 # dynamic-S2 / TSP data movement
