@@ -343,8 +343,8 @@ def sp_prefill_block(model, args, peaks, rank, world, local):
         for _ in range(max(3, args.warmup) if not args.profile else 1):
             est = step()[0]
         # at least --sp-steps steps, and long enough for >= 20 nvidia-smi clock samples (a query takes
-        # ~0.5 s on an 8-GPU box): ~12 s of timed steps, capped at 64 steps; same count on every rank
-        n_steps = torch.tensor([max(args.sp_steps, min(64, int(12000.0 / max(est, 1.0)) + 1))], device="cuda")
+        # ~0.75 s on an 8-GPU box): ~20 s of timed steps, capped at 80 steps; same count on every rank
+        n_steps = torch.tensor([max(args.sp_steps, min(80, int(20000.0 / max(est, 1.0)) + 1))], device="cuda")
         dist.all_reduce(n_steps, op=dist.ReduceOp.MAX)
         n_steps = int(n_steps)
         dist.barrier(); torch.cuda.synchronize()
