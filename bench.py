@@ -517,7 +517,11 @@ def run_ours(args):
     batched = None
     if not (args.profile or args.no_video):
         try:
-            batched = batched_decode_block(model, peaks, ids_h, pixels_d)
+            batched = batched_decode_block(model, peaks, ids_h, pixels_d, slots=8)
+            batched["more_slots"] = [
+                {k: v for k, v in batched_decode_block(model, peaks, ids_h, pixels_d, slots=n).items()
+                 if k in ("slots", "aggregate_tok_s", "ms_per_step", "frac_of_hbm_peak", "all_slots_agree")}
+                for n in (32,)]
         except Exception as e:
             batched = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
             torch.cuda.synchronize()
