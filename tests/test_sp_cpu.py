@@ -144,3 +144,16 @@ def test_sp_registry_defaults_off():
     sp.set_sequence_parallel_group(None)
     assert not sp.sequence_parallel_enabled()  # no process group initialised in this process
     sp.set_sequence_parallel_group(None, enabled=False)
+
+
+def test_serving_page_allocator():
+    """host bookkeeping of the continuous-batching engine (vila_b200/serving.py)"""
+    from vila_b200.serving import PageAllocator
+    a = PageAllocator(6)
+    p1 = a.alloc(2)
+    p2 = a.alloc(3)
+    assert p1 == [0, 1] and p2 == [2, 3, 4] and a.available == 1
+    with pytest.raises(MemoryError):
+        a.alloc(2)
+    a.release(p1)
+    assert a.available == 3 and sorted(a.alloc(3)) == [0, 1, 5]

@@ -45,10 +45,36 @@ class _SlotCache:
         return self.pool[layer, 1]
 
 
-class BatchedDecoder:
-    """`slots` concurrent greedy decodes of one Qwen2ForCausalLM over a shared paged pool."""
+class PageAllocator:
+    """Free list over the physical pages of the shared pool (host-side bookkeeping only)."""
 
-    def __init__(self, llm, slots: int = 8, max_tokens_per_slot: int = 2048, max_new: int = 1024):
+    def __init__(self, n_pages: int):
+        self.free: List[int] = list(range(n_pages - 1, -1, -1))  # pop() hands out page 0 first
+        self.n_pages = n_pages
+
+    def alloc(self, n: int) -> List[int]:
+        if n > len(self.free):
+            raise MemoryError(f"KV pool exhausted: {n} pages wanted, {len(self.free)} free of {self.n_pages}")
+        return [self.free.pop() for _ in range(n)]
+
+    def release(self, pages: Sequence[int]) -> None:
+        self.free.extend(reversed(list(pages)))
+
+    @property
+    def available(self) -> int:
+        return len(self.free)
+
+
+class BatchedDecoder:
+    """`slots` concurrent greedy decodes of one Qwen2ForCausalLM over a shared paged pool.
+
+    Pages are handed out on demand (PageAllocator): a slot holds ceil(tokens / 128) pages, grows page by
+    page while it decodes and returns them when it is released, so `total_pages` can be smaller than
+    slots * pages_per_slot (long and short requests share the pool).  The page-table rows live on the
+    device and are read by the kernels at every launch: changing them needs no graph re-capture."""
+
+    def __init__(self, llm, slots: int = 8, max_tokens_per_slot: int = 2048, max_new: int = 1024,
+                 total_pages: Optional[int] = None):
         cfg = llm.config
         self.llm, self.slots = llm, slots
         dev, dt = llm.device, llm.dtype
@@ -56,10 +82,13 @@ class BatchedDecoder:
         assert D == 128, "batched decode attention is specialised for head_dim 128"
         self.pages_per_slot = (max_tokens_per_slot + PAGE - 1) // PAGE
         assert self.pages_per_slot <= 32, "vila_decode_attention_batch serves contexts up to 4096 tokens"
-        P = slots * self.pages_per_slot
+        P = total_pages if total_pages is not None else slots * self.pages_per_slot
         self.pool = torch.zeros(cfg.num_hidden_layers, 2, P, PAGE, Hkv, D, device=dev, dtype=dt)
-        # static partition of the pool (any permutation works: the kernels follow the table)
-        self.page_tables = torch.arange(P, dtype=torch.int32, device=dev).view(slots, self.pages_per_slot).contiguous()
+        self.allocator = PageAllocator(P)
+        self.slot_pages: List[List[int]] = [[] for _ in range(slots)]
+        # unassigned entries point at page 0; they are never dereferenced (tokens beyond a slot's length)
+        self.page_tables = torch.zeros(slots, self.pages_per_slot, dtype=torch.int32, device=dev)
+        self._pos_host = [-1] * slots  # host mirror of `positions` (advanced by run())
         self.positions = torch.full((slots,), -1, dtype=torch.int32, device=dev)  # < 0: idle slot
         self.x = torch.zeros(slots, cfg.hidden_size, device=dev, dtype=dt)
         self.attn = torch.zeros(slots, Hq * D, device=dev, dtype=dt)
@@ -76,8 +105,9 @@ class BatchedDecoder:
         """Prefill `inputs_embeds` [S, hidden] into the slot's pages and seed its decode state."""
         llm = self.llm
         S = inputs_embeds.shape[0]
+        assert S + 1 <= self.pages_per_slot * PAGE, "prompt longer than a slot"
+        self._ensure_pages(slot, S + 1)
         cache = _SlotCache(self.pool, self.page_tables[slot])
-        assert S + 1 <= cache.max_tokens, "prompt longer than the slot"
         hid = llm.prefill_hidden(inputs_embeds, cache)
         logits = llm.logits_from_hidden(hid[-1:])
         tok = torch.argmax(logits[0].float())
@@ -86,9 +116,23 @@ class BatchedDecoder:
         self.step_idx[slot, 0] = 1
         self.x[slot] = llm.model.embed_tokens.weight[tok]
         self.positions[slot] = S  # position of the token just chosen == tokens cached so far
+        self._pos_host[slot] = S
 
     def release(self, slot: int) -> None:
         self.positions[slot] = -1
+        self._pos_host[slot] = -1
+        self.allocator.release(self.slot_pages[slot])
+        self.slot_pages[slot] = []
+
+    def _ensure_pages(self, slot: int, n_tokens: int) -> None:
+        """make sure the slot owns pages for its first n_tokens tokens"""
+        need = min(self.pages_per_slot, (n_tokens + PAGE - 1) // PAGE) - len(self.slot_pages[slot])
+        if need > 0:
+            new = self.allocator.alloc(need)
+            first = len(self.slot_pages[slot])
+            self.slot_pages[slot].extend(new)
+            self.page_tables[slot, first:first + need] = torch.tensor(new, dtype=torch.int32,
+                                                                      device=self.page_tables.device)
 
     # ---- one decode step for every active slot ----------------------------------------------------
     def _step(self) -> None:
@@ -119,6 +163,10 @@ class BatchedDecoder:
     def run(self, n_tokens: int) -> None:
         if self.graph is None:
             raise RuntimeError("call capture() (with every slot idle) before run()")
+        for s_ in range(self.slots):  # pages for the tokens this call will append
+            if self._pos_host[s_] >= 0:
+                self._ensure_pages(s_, self._pos_host[s_] + n_tokens + 1)
+                self._pos_host[s_] += n_tokens
         for _ in range(n_tokens):
             self.graph.replay()
 
@@ -147,11 +195,12 @@ class BatchedDecoder:
 @torch.inference_mode()
 def generate_batch(llm, prompts: Sequence[torch.Tensor], max_new_tokens: int, eos_token_ids: Sequence[int] = (),
                    slots: int = 8, max_tokens_per_slot: int = 2048, check_every: int = 8,
-                   decoder: Optional[BatchedDecoder] = None) -> List[List[int]]:
+                   decoder: Optional[BatchedDecoder] = None, total_pages: Optional[int] = None) -> List[List[int]]:
     """Greedy-decode `prompts` (list of inputs_embeds [S_i, hidden]) with continuous batching: at most
     `slots` requests in flight; a finished request (EOS or max_new_tokens) frees its slot for the next
     one in the queue.  Returns the new ids per request (EOS included), in request order."""
-    dec = decoder or BatchedDecoder(llm, slots, max_tokens_per_slot, max_new=max_new_tokens)
+    dec = decoder or BatchedDecoder(llm, slots, max_tokens_per_slot, max_new=max_new_tokens,
+                                    total_pages=total_pages)
     dec.capture()
     cap = dec.pages_per_slot * PAGE
     for p in prompts:
@@ -171,6 +220,10 @@ def generate_batch(llm, prompts: Sequence[torch.Tensor], max_new_tokens: int, eo
     while queue or owner:
         for s in range(dec.slots):
             if s not in owner and queue:
+                # admit only when the pool can hold the prompt and the request's whole budget
+                need = (prompts[queue[0]].shape[0] + max_new_tokens + check_every + PAGE - 1) // PAGE
+                if need > dec.allocator.available and owner:
+                    break  # wait for a running request to finish and return its pages
                 r = queue.popleft()
                 dec.admit(s, prompts[r])
                 owner[s] = r
