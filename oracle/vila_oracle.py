@@ -406,6 +406,9 @@ def apply_rope(q, k, cos, sin):
     return q * cos + rotate_half(q) * sin, k * cos + rotate_half(k) * sin
 
 
+SCORE_BUDGET = 1 << 28  # elements of one attention-score block (memory bound only; the result does not depend on it)
+
+
 def qwen2_attention(x, p, prefix: str, cfg: Qwen2Cfg, position_ids, past_kv=None):
     """Qwen2Attention.forward (modeling_qwen2.py:191-310): q/k/v proj (+bias), RoPE, KV cache
     append, repeat_kv (:179-188), causal softmax(QK^T/sqrt(d)) in fp32, PV, o_proj (no bias)."""
@@ -424,17 +427,27 @@ def qwen2_attention(x, p, prefix: str, cfg: Qwen2Cfg, position_ids, past_kv=None
     kk = k.repeat_interleave(rep, dim=0)
     vv = v.repeat_interleave(rep, dim=0)
     Sk = kk.shape[1]
-    mask = torch.full((S, Sk), float("-inf"), dtype=torch.float32, device=x.device)
-    mask = torch.triu(mask, diagonal=Sk - S + 1)
-    # Same arithmetic per head; heads are processed in groups only to bound the [h, S, Sk] score
-    # tensor for long sequences (64-frame video: S = 16.5K -> 1 GB per head in fp32).
-    hstep = max(1, min(H, (1 << 28) // max(1, S * Sk)))
+    # Same arithmetic per (head, query row); heads and query rows are processed in blocks only to bound
+    # the [h, q, Sk] score tensor for long sequences (64-frame video: S = 16.5K -> 1 GB per head in fp32;
+    # 256 frames: S = 65.8K -> 17 GB per head, hence the row blocks).
+    hstep = max(1, min(H, SCORE_BUDGET // max(1, S * Sk)))
+    qstep = S if S * Sk <= SCORE_BUDGET else max(1, SCORE_BUDGET // Sk)
+    kv_idx = torch.arange(Sk, device=x.device)
     outs = []
     for h0 in range(0, H, hstep):
-        att = torch.matmul(q[h0:h0 + hstep], kk[h0:h0 + hstep].transpose(1, 2)) / math.sqrt(D)  # :273
-        att = att + mask.to(att.dtype)
-        att = F.softmax(att, dim=-1, dtype=torch.float32).to(q.dtype)  # :290
-        outs.append(torch.matmul(att, vv[h0:h0 + hstep]))
+        rows = []
+        for q0 in range(0, S, qstep):
+            q1 = min(S, q0 + qstep)
+            att = torch.matmul(q[h0:h0 + hstep, q0:q1], kk[h0:h0 + hstep].transpose(1, 2)) / math.sqrt(D)  # :273
+            # causal mask: query row i (global position Sk - S + i) sees kv <= its position
+            mask = torch.zeros((q1 - q0, Sk), dtype=torch.float32, device=x.device)
+            mask.masked_fill_(kv_idx[None, :] > (torch.arange(q0, q1, device=x.device)[:, None] + (Sk - S)),
+                              float("-inf"))
+            att = att + mask.to(att.dtype)
+            att = F.softmax(att, dim=-1, dtype=torch.float32).to(q.dtype)  # :290
+            rows.append(torch.matmul(att, vv[h0:h0 + hstep]))
+            del att, mask
+        outs.append(torch.cat(rows, dim=1) if len(rows) > 1 else rows[0])
     o = torch.cat(outs, dim=0).transpose(0, 1).reshape(S, H * D)
     return F.linear(o, p[prefix + "o_proj.weight"]), new_kv
 

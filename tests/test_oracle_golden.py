@@ -84,3 +84,25 @@ def test_flat_square_edge_cases():
     assert torch.equal(y[0, 0, 0], torch.cat([x[0, 0, 0], x[0, 0, 1], x[0, 1, 0], x[0, 1, 1]]))
     assert y[0, 1, 2, 2:].abs().sum() == 0 and torch.equal(y[0, 1, 2, :2], x[0, 2, 4])
     assert O.flat_square(torch.zeros(1, 4, 4, 2), 3).shape == (1, 2, 2, 18)
+
+
+def test_oracle_attention_blocking_does_not_change_results():
+    """the head / query-row blocking of the oracle's attention (a memory bound for 16K-66K token
+    sequences) computes the same function: tiny budgets give the same logits up to fp32 BLAS summation
+    order (1e-5), with and without a cache"""
+    d = torch.load(G / "qwen2_tiny.pt")
+    cfg = O.Qwen2Cfg(head_dim=16, **d["cfg"])
+    p = d["weights"]
+    emb = d["emb"][0]
+    want, past = O.qwen2_forward(emb, p, cfg)
+    step, _ = O.qwen2_forward(emb[-3:], p, cfg, past=[(k[:, :-3], v[:, :-3]) for k, v in past])
+    old = O.SCORE_BUDGET
+    try:
+        for budget in (1, 7 * emb.shape[0], 3 * emb.shape[0] * emb.shape[0]):
+            O.SCORE_BUDGET = budget
+            got, _ = O.qwen2_forward(emb, p, cfg)
+            assert (got - want).abs().max().item() < 1e-5, budget
+            got2, _ = O.qwen2_forward(emb[-3:], p, cfg, past=[(k[:, :-3], v[:, :-3]) for k, v in past])
+            assert (got2 - step).abs().max().item() < 1e-5, budget
+    finally:
+        O.SCORE_BUDGET = old

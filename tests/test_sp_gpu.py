@@ -136,3 +136,74 @@ def test_sp_public_api_generate_and_forward(world, n_frames):
         assert got_ids == ret[0][1]
         n_same = next((i for i, (a, b) in enumerate(zip(got_ids, ref_ids)) if a != b), len(ref_ids))
         assert n_same >= 1, (got_ids, ref_ids)
+
+
+def _cfg5_worker(rank, world, port, ret):
+    """BASELINE configs[4] at its NAMED size on one GPU: 256 frames -> S = 65,814 tokens through the
+    sequence-parallel prefill code path (world 1: two zigzag chunks, zigzag page order) against the oracle
+    evaluated on the device (fp32 = truth, bf16 = the reference's own numerics)."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        from oracle import vila_oracle as O
+        from tests.helpers import oracle_from_state_dict
+        from vila_b200 import sp
+        from vila_b200.model import LlavaLlamaModel, nvila_video_8b
+        cfg = nvila_video_8b()
+        model = LlavaLlamaModel(cfg, device="cuda").init_random(0, device_rng=True)
+        llm = model.llm
+        g = torch.Generator(device="cuda").manual_seed(11)
+        frames = torch.randn(256, 3, 448, 448, device="cuda", generator=g).to(torch.bfloat16)
+        vid = model.encoders["video"]([frames], {})[0]                      # [256*257, hidden] bf16
+        text = llm.model.embed_tokens.weight[torch.arange(100, 122, device="cuda")]
+        seq = torch.cat([text[:14], vid, text[14:]], 0)
+        S = seq.shape[0]
+        del frames, vid
+        # CUDA path: the SP runner (what LlavaLlamaModel.generate uses under set_sequence_parallel_group)
+        runner = sp.SequenceParallelPrefill(llm)
+        plan = sp.make_plan(S, world, rank)
+        padded = seq.new_zeros((plan.padded_len, seq.shape[1]))
+        padded[:S] = seq
+        hid_local, pool = runner.prefill_hidden(plan.extract_local(padded), plan)
+        logits = runner.last_token_logits(hid_local, plan).float().cpu()
+        del hid_local, pool, padded
+        torch.cuda.empty_cache()
+        # oracle on the device, LLM weights only
+        sd = {k: v for k, v in model.state_dict().items() if k.startswith("llm.")}
+        outs = []
+        for dt in (torch.float32, torch.bfloat16):
+            p = {k[4:]: v.to(dt) for k, v in sd.items()}
+            lc = cfg.llm_cfg
+            ocfg = O.Qwen2Cfg(lc.hidden_size, lc.intermediate_size, lc.num_hidden_layers, lc.num_attention_heads,
+                              lc.num_key_value_heads, lc.vocab_size, lc.rms_norm_eps, lc.rope_theta, lc.head_dim)
+            with torch.inference_mode():
+                lg, _ = O.qwen2_forward(seq.to(dt), p, ocfg, last_only=True)
+            outs.append(lg.float().cpu())
+            del p, lg
+            torch.cuda.empty_cache()
+        ret[rank] = (S, logits, outs[0], outs[1])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg5_named_size_matches_oracle():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    free, total = torch.cuda.mem_get_info()
+    if total < 150 * 2 ** 30:
+        pytest.skip("needs a 180 GB B200 (fp32 oracle of the 8B model at S = 65.8K)")
+    import torch.multiprocessing as mp
+    from tests.helpers import check_close
+    ret = mp.Manager().dict()
+    mp.spawn(_cfg5_worker, args=(1, _free_port(), ret), nprocs=1, join=True)
+    S, logits, l32, l16 = ret[0]
+    assert S == 256 * 257 + 22
+    check_close("cfg5 SP prefill last-token logits (S = 65,814, 28 layers)", logits, l32, l16, factor=1.3)
+    top2 = torch.topk(l32[0], 2).values
+    if float(top2[0] - top2[1]) > 3 * 2 ** -8 * float(l32.abs().max()):
+        assert int(torch.argmax(logits[0])) == int(torch.argmax(l32[0]))
