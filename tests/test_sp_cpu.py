@@ -157,3 +157,78 @@ def test_serving_page_allocator():
         a.alloc(2)
     a.release(p1)
     assert a.available == 3 and sorted(a.alloc(3)) == [0, 1, 5]
+
+
+class _FakeDecoder:
+    """Stands in for serving.BatchedDecoder on a machine without a GPU: same host-visible surface
+    (slots, allocator, admit / run / release / generated), a deterministic token rule instead of kernels:
+    request with prompt length S emits S, S+1, S+2, ... so EOS can be placed at a chosen step."""
+
+    def __init__(self, slots, pages_per_slot, total_pages):
+        from vila_b200.serving import PageAllocator
+        self.slots, self.pages_per_slot = slots, pages_per_slot
+        self.allocator = PageAllocator(total_pages)
+        self.slot_pages = [[] for _ in range(slots)]
+        self.state = [None] * slots
+        self.max_in_flight = 0
+        self.admitted = []
+
+    def capture(self):
+        pass
+
+    def _ensure(self, s, n_tokens):
+        need = min(self.pages_per_slot, -(-n_tokens // 128)) - len(self.slot_pages[s])
+        if need > 0:
+            self.slot_pages[s].extend(self.allocator.alloc(need))
+
+    def admit(self, s, emb):
+        assert self.state[s] is None
+        S = emb.shape[0]
+        self._ensure(s, S + 1)
+        self.state[s] = [S, [S]]  # (tokens cached, generated ids)
+        self.admitted.append((s, S))
+        self.max_in_flight = max(self.max_in_flight, sum(x is not None for x in self.state))
+
+    def run(self, n):
+        for s, st in enumerate(self.state):
+            if st is not None:
+                self._ensure(s, st[0] + n + 1)
+                for _ in range(n):
+                    st[1].append(st[1][-1] + 1)
+                st[0] += n
+
+    def generated(self, s):
+        return list(self.state[s][1])
+
+    def release(self, s):
+        self.allocator.release(self.slot_pages[s])
+        self.slot_pages[s], self.state[s] = [], None
+
+
+def test_continuous_batching_scheduler_host_logic():
+    """generate_batch (vila_b200/serving.py): admission order, slot reuse, EOS cut (EOS included),
+    max_new_tokens cut, admission held back while the pool cannot hold a request's whole budget, every
+    page returned at the end."""
+    import torch
+    from vila_b200.serving import generate_batch
+    lens = [100, 300, 50, 700, 120, 260, 900]
+    prompts = [torch.zeros(n, 4) for n in lens]
+    dec = _FakeDecoder(slots=3, pages_per_slot=8, total_pages=12)
+    # request r emits lens[r], lens[r]+1, ...: EOS ids hit request 0 at its 6th token and request 3 at its 1st
+    out = generate_batch(None, prompts, max_new_tokens=20, eos_token_ids=(105, 700), slots=3, check_every=4,
+                         decoder=dec)
+    assert out[0] == [100, 101, 102, 103, 104, 105]
+    assert out[3] == [700]
+    for r in (1, 2, 4, 5, 6):
+        assert out[r] == list(range(lens[r], lens[r] + 20))
+    assert [s for _, s in dec.admitted] == lens              # FIFO admission
+    assert dec.max_in_flight <= 3 and len({s for s, _ in dec.admitted}) == 3   # slots are reused
+    assert dec.allocator.available == 12 and all(x is None for x in dec.state)
+    # a pool too small for two budgets at once serialises the requests instead of overflowing
+    dec2 = _FakeDecoder(slots=3, pages_per_slot=8, total_pages=8)
+    out2 = generate_batch(None, prompts[:4], max_new_tokens=20, eos_token_ids=(), slots=3, check_every=4, decoder=dec2)
+    assert [len(o) for o in out2] == [20] * 4 and dec2.allocator.available == 8
+    # a request that can never fit a slot is refused up front
+    with pytest.raises(ValueError):
+        generate_batch(None, [torch.zeros(1020, 4)], max_new_tokens=20, slots=1, check_every=4,
+                       decoder=_FakeDecoder(1, 8, 8))

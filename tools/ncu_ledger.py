@@ -142,13 +142,14 @@ qkv1 = rn(NQ)
 out1 = torch.zeros(Hq * D, dtype=bf, device=dev)
 ws = torch.zeros(Hkv * 64 * (Hq // Hkv) * (D + 2), dtype=torch.float32, device=dev)
 cnt = torch.zeros(Hkv, dtype=torch.int32, device=dev)
-for ctx, splits in ((279, 8), (16448, 64), (65814, 64)):
+for ctx, splits in ((279, 0), (279, 8), (16448, 64), (65814, 64)):
     npg = (ctx + 1 + 127) // 128 + 1
     kp = rn(npg, 128, Hkv, D)
     vp = rn(npg, 128, Hkv, D)
     ptd = torch.arange(npg, dtype=torch.int32, device=dev)
     pos1 = torch.tensor([ctx], dtype=torch.int32, device=dev)
-    entry("decode_attn ctx=%d splits=%d" % (ctx, splits), 2 * 2 * (ctx + 1) * Hkv * D, 4 * (ctx + 1) * Hq * D,
+    entry(("decode_attn ctx=%d splits=%d" % (ctx, splits)) if splits else ("decode_attn_head (one CTA per query head) ctx=%d" % ctx),
+          2 * 2 * (ctx + 1) * Hkv * D, 4 * (ctx + 1) * Hq * D,
           lambda kp=kp, vp=vp, ptd=ptd, pos1=pos1, splits=splits: ops.decode_attention(
               qkv1, pos1, kp, vp, ptd, out1, ws, cnt, inv, Hq, Hkv, D, splits, D ** -0.5))
 o_part = torch.zeros(64 * Hq * D, dtype=torch.float32, device=dev)
@@ -164,6 +165,25 @@ for ctx, splits, st in ((16448, 33, 512), (65814, 37, 1792)):
           2 * 2 * (ctx + 1) * Hkv * D, 4 * (ctx + 1) * Hq * D,
           lambda kp=kp, vp=vp, ptd=ptd, pos1=pos1, splits=splits, st=st: ops.decode_attention_split(
               qkv1.clone(), pos1, kp, vp, ptd, out1, o_part, lse_b, inv, Hq, Hkv, D, splits, st, D ** -0.5))
+# continuous batching: 8 slots of ~300 tokens over one shared pool, and the M = 8 weight-streaming GEMM beside it
+Bs = 8
+pool_k, pool_v = rn(Bs * 4, 128, Hkv, D), rn(Bs * 4, 128, Hkv, D)
+pts = torch.arange(Bs * 4, dtype=torch.int32, device=dev).view(Bs, 4).contiguous()
+pos_b = torch.tensor([279 + 7 * i for i in range(Bs)], dtype=torch.int32, device=dev)
+qkv_b = rn(Bs, NQ)
+out_b = torch.zeros(Bs, Hq * D, dtype=bf, device=dev)
+entry("decode_attention_batch 8 slots ctx=279..328 (shared paged pool)", 2 * 2 * int(pos_b.sum() + Bs) * Hkv * D,
+      4 * int(pos_b.sum() + Bs) * Hq * D,
+      lambda: ops.decode_attention_batch(qkv_b, pos_b, pool_k, pool_v, pts, out_b, inv, Hq, Hkv, D, D ** -0.5))
+x8 = rn(Bs, Hd, s=0.05)
+entry("gemm_skinny gate/up SwiGLU M=8 N=37888 K=3584 (batched decode)", 2 * (Bs * Hd + 2 * I * Hd + Bs * I),
+      2 * Bs * 2 * I * Hd, lambda: ops.linear(x8, wgu, swiglu=True, static_w=True))
+# preprocessing (f2): 1920x1080 uint8 frame -> 1344x896 -> six 448^2 bf16 tiles, PIL-exact
+src_img = torch.randint(0, 256, (1080, 1920, 3), dtype=torch.uint8, device=dev)
+tiles_out = torch.zeros(6, 3, 448, 448, dtype=bf, device=dev)
+entry("resize_bicubic_tiles[2 launches: resize_h, resize_v_norm] 1920x1080 -> 1344x896 -> 6 tiles",
+      1080 * 1920 * 3 + 2 * 1080 * 1344 * 3 + 896 * 1344 * 3 * 2, 0,
+      lambda: ops.resize_bicubic_tiles(src_img, 1344, 896, tiles_out, 448, 0, 0.5, 0.5))
 # long / batched shapes
 Sv = 64 * 257 + 22
 npg = (Sv + 127) // 128

@@ -6,6 +6,7 @@ utilisation, registers, shared memory, and beside them the ALGORITHMIC bytes / f
 import csv
 import io
 import json
+import re
 import subprocess
 import sys
 from pathlib import Path
@@ -75,7 +76,8 @@ for r in rows[2:]:
 # map launches to ledger entries in order; an entry may own several launches (label says "[3 launches")
 out, i = [], 0
 for e in labels:
-    n = 3 if "[3 launches" in e["label"] else 1
+    mm = re.search(r"\[(\d+) launches", e["label"])
+    n = int(mm.group(1)) if mm else 1
     mine = launches[i:i + n]
     i += n
     if not mine:
