@@ -91,32 +91,35 @@ struct S2Args {
   int sh[4], sw[4], tile0[4];
   int out_bh, out_bw;
 };
+// I = index type: uint32_t whenever the item count fits (always for real images) — the 64-bit divisions
+// of the generic version made the kernel instruction-issue bound (ncu r02: 76 % issue active, 0.19 of HBM)
+template <typename I>
 __global__ void s2_merge_kernel(const __nv_bfloat16* __restrict__ tiles,
                                 __nv_bfloat16* __restrict__ out, S2Args a) {
   griddep_launch_dependents();
   griddep_wait();
-  const int Cv = a.C / 8;
-  const int OH = a.out_bh * a.side, OW = a.out_bw * a.side;
-  const long total = (long)OH * OW * a.n_scales * Cv;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long)gridDim.x * blockDim.x) {
-    int cv = idx % Cv;
-    long t = idx / Cv;
-    int s = t % a.n_scales;
-    t /= a.n_scales;
-    int ox = t % OW;
-    int oy = t / OW;
-    const int IH = a.sh[s] * a.side, IW = a.sw[s] * a.side;
+  const I Cv = a.C / 8;
+  const I OH = a.out_bh * a.side, OW = a.out_bw * a.side;
+  const I total = OH * OW * (I)a.n_scales * Cv;
+  const I side = a.side;
+  for (I idx = blockIdx.x * (I)blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+    const I cv = idx % Cv;
+    I t = idx / Cv;
+    const int s = (int)(t % (I)a.n_scales);
+    t /= (I)a.n_scales;
+    const I ox = t % OW;
+    const I oy = t / OW;
+    const I IH = a.sh[s] * a.side, IW = a.sw[s] * a.side;
     // adaptive_avg_pool window: [floor(o*I/O), ceil((o+1)*I/O))
-    const int y0 = (int)(((long)oy * IH) / OH), y1 = (int)((((long)oy + 1) * IH + OH - 1) / OH);
-    const int x0 = (int)(((long)ox * IW) / OW), x1 = (int)((((long)ox + 1) * IW + OW - 1) / OW);
+    const I y0 = (oy * IH) / OH, y1 = ((oy + 1) * IH + OH - 1) / OH;
+    const I x0 = (ox * IW) / OW, x1 = ((ox + 1) * IW + OW - 1) / OW;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int y = y0; y < y1; ++y) {
-      for (int x = x0; x < x1; ++x) {
-        const int tile = a.tile0[s] + (y / a.side) * a.sw[s] + (x / a.side);
-        const int tok = (y % a.side) * a.side + (x % a.side);
+    for (I y = y0; y < y1; ++y) {
+      for (I x = x0; x < x1; ++x) {
+        const I tile = a.tile0[s] + (y / side) * a.sw[s] + (x / side);
+        const I tok = (y % side) * side + (x % side);
         const uint4 v = ldg_v4(reinterpret_cast<const uint4*>(
-                                   tiles + ((long)tile * a.side * a.side + tok) * a.C) + cv);
+                                   tiles + ((size_t)tile * side * side + tok) * a.C) + cv);
         acc[0] += bf_lo(v.x); acc[1] += bf_hi(v.x); acc[2] += bf_lo(v.y); acc[3] += bf_hi(v.y);
         acc[4] += bf_lo(v.z); acc[5] += bf_hi(v.z); acc[6] += bf_lo(v.w); acc[7] += bf_hi(v.w);
       }
@@ -127,10 +130,10 @@ __global__ void s2_merge_kernel(const __nv_bfloat16* __restrict__ tiles,
     o.y = pack_bf16(acc[2] * inv, acc[3] * inv);
     o.z = pack_bf16(acc[4] * inv, acc[5] * inv);
     o.w = pack_bf16(acc[6] * inv, acc[7] * inv);
-    const int otile = (oy / a.side) * a.out_bw + (ox / a.side);
-    const int otok = (oy % a.side) * a.side + (ox % a.side);
+    const I otile = (oy / side) * a.out_bw + (ox / side);
+    const I otok = (oy % side) * side + (ox % side);
     uint4* dst = reinterpret_cast<uint4*>(
-        out + ((long)otile * a.side * a.side + otok) * ((long)a.n_scales * a.C) + (long)s * a.C);
+        out + ((size_t)otile * side * side + otok) * ((size_t)a.n_scales * a.C) + (size_t)s * a.C);
     dst[cv] = o;
   }
 }
@@ -185,6 +188,47 @@ __global__ void tsp_pool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
       sw_acc += bf16_round(sh_acc / ph);
     }
     out[idx] = __float2bfloat16(sw_acc / pw);
+  }
+}
+
+// the same pooling, 8 channels per thread (16-byte loads / stores, 32-bit index math): the scalar version
+// above moves 2 bytes per load and sat at 0.19 of HBM.  Same order of roundings per channel.
+__global__ void tsp_pool_v8_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int T, int h,
+                                   int w, int Cv, int pt, int ph, int pw) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const uint32_t ho = h / ph, wo = w / pw;
+  const uint32_t total = (uint32_t)(T / pt) * ho * wo * Cv;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const uint32_t cv = idx % Cv;
+    uint32_t t = idx / Cv;
+    const uint32_t xo = t % wo;
+    t /= wo;
+    const uint32_t yo = t % ho, to = t / ho;
+    float sw_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c3 = 0; c3 < pw; ++c3) {
+      float sh_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c2 = 0; c2 < ph; ++c2) {
+        float st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const size_t row0 = ((size_t)(to * pt) * h + (yo * ph + c2)) * w + (xo * pw + c3);
+#pragma unroll 4
+        for (int c1 = 0; c1 < pt; ++c1) {
+          const uint4 v = ldg_stream(x + (row0 + (size_t)c1 * h * w) * Cv + cv);
+          st[0] += bf_lo(v.x); st[1] += bf_hi(v.x); st[2] += bf_lo(v.y); st[3] += bf_hi(v.y);
+          st[4] += bf_lo(v.z); st[5] += bf_hi(v.z); st[6] += bf_lo(v.w); st[7] += bf_hi(v.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sh_acc[k] += bf16_round(st[k] / pt);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sw_acc[k] += bf16_round(sh_acc[k] / ph);
+    }
+    uint4 o;
+    o.x = pack_bf16(sw_acc[0] / pw, sw_acc[1] / pw);
+    o.y = pack_bf16(sw_acc[2] / pw, sw_acc[3] / pw);
+    o.z = pack_bf16(sw_acc[4] / pw, sw_acc[5] / pw);
+    o.w = pack_bf16(sw_acc[6] / pw, sw_acc[7] / pw);
+    out[idx] = o;
   }
 }
 
@@ -457,7 +501,11 @@ int s2_merge(const __nv_bfloat16* tiles, __nv_bfloat16* out, int side, int C, in
     if (!share_tile) t0 += a.sh[s] * a.sw[s];
   }
   const long total = (long)out_bh * side * out_bw * side * n_scales * (C / 8);
-  VB_CUDA(launch_pdl(s2_merge_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, tiles, out, a));
+  if (total < (1L << 31)) {
+    VB_CUDA(launch_pdl(s2_merge_kernel<uint32_t>, dim3(grid_for(total, 256)), dim3(256), 0, stream, tiles, out, a));
+  } else {
+    VB_CUDA(launch_pdl(s2_merge_kernel<long>, dim3(grid_for(total, 256)), dim3(256), 0, stream, tiles, out, a));
+  }
   return 0;
 }
 
@@ -477,6 +525,12 @@ int tsp_pool(const __nv_bfloat16* x, __nv_bfloat16* out, int T, int h, int w, in
            "tsp_pool: pool sizes (%d,%d,%d) must divide (%d,%d,%d)", pt, ph, pw, T, h, w);
   const long total = (long)(T / pt) * (h / ph) * (w / pw) * C;
   if (total == 0) return 0;
+  if (C % 8 == 0 && total / 8 < (1L << 31) && (long)T * h * w < (1L << 31) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    VB_CUDA(launch_pdl(tsp_pool_v8_kernel, dim3(grid_for(total / 8, 256)), dim3(256), 0, stream,
+                       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), T, h, w, C / 8, pt, ph, pw));
+    return 0;
+  }
   VB_CUDA(launch_pdl(tsp_pool_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, x, out, T, h, w, C, pt, ph, pw));
   return 0;
 }
