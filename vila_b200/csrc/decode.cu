@@ -677,25 +677,39 @@ decode_attn_head_kernel(DecodeAttnBatchArgs args) {
 // (tcgen05 FMHA kernel in split mode).  out[h, :] = sum_s w_s * O_s[h, :], w_s = 2^(lse_s - max) / sum.
 // Splits are summed in index order (deterministic).
 // ------------------------------------------------------------------------------------------------
+// The split weights are computed once per CTA from lse values fetched in parallel, and the partial rows are
+// fetched 16 at a time: the first version walked the splits three times with one dependent load per step
+// (ncu r02: 23 us for 0.5 MB, a chain of 3 x 33 DRAM latencies).  Same summation order -> same result.
+constexpr int kCombineMaxSplits = 256;
 __global__ void decode_combine_kernel(const float* __restrict__ o_partial, const float* __restrict__ lse,
                                       __nv_bfloat16* __restrict__ out, int Hq, int D, int splits) {
+  __shared__ float w_s[kCombineMaxSplits];
   griddep_launch_dependents();
   griddep_wait();
   const int h = blockIdx.x;  // query head (= kv head * G + g, the layout of the partials' [Hkv][G])
+  for (int s = threadIdx.x; s < splits; s += blockDim.x) w_s[s] = __ldcg(lse + (long)s * Hq + h);
+  __syncthreads();
   float mx = -INFINITY;
-  for (int s = 0; s < splits; ++s) mx = fmaxf(mx, lse[(long)s * Hq + h]);
-  float den = 0.f;
-  for (int s = 0; s < splits; ++s) {
-    const float v = lse[(long)s * Hq + h];
-    den += (v == -INFINITY) ? 0.f : exp2f(v - mx);
+  for (int s = 0; s < splits; ++s) mx = fmaxf(mx, w_s[s]);
+  __syncthreads();
+  for (int s = threadIdx.x; s < splits; s += blockDim.x) {
+    const float v = w_s[s];
+    w_s[s] = (v == -INFINITY) ? 0.f : exp2f(v - mx);
   }
+  __syncthreads();
+  float den = 0.f;
+  for (int s = 0; s < splits; ++s) den += w_s[s];
   const float inv = den > 0.f ? 1.f / den : 0.f;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const float v = lse[(long)s * Hq + h];
-      const float w = (v == -INFINITY) ? 0.f : exp2f(v - mx);
-      acc += w * o_partial[((long)s * Hq + h) * D + d];
+    const float* src = o_partial + (long)h * D + d;
+    for (int s0 = 0; s0 < splits; s0 += 16) {
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = (s0 + j < splits) ? __ldcg(src + (long)(s0 + j) * Hq * D) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (s0 + j < splits) acc += w_s[s0 + j] * o[j];
     }
     out[(long)h * D + d] = __float2bfloat16(acc * inv);
   }
@@ -823,6 +837,7 @@ int decode_attention_split(const DecodeAttnSplitParams& p, cudaStream_t stream) 
   rc = fmha_decode_split(f, p.position, p.split_tokens, p.o_partial, p.lse, p.counters, stream);
   if (rc) return rc;
   if (p.counters != nullptr) return 0;  // combined by the last split CTA of every KV head
+  VB_CHECK(p.num_splits <= kCombineMaxSplits, "decode_attention_split: at most %d splits", kCombineMaxSplits);
   VB_CUDA(launch_pdl(decode_combine_kernel, dim3(p.Hq), dim3(128), 0, stream,
                      static_cast<const float*>(p.o_partial), static_cast<const float*>(p.lse), p.out,
                      p.Hq, p.D, p.num_splits));
