@@ -233,6 +233,24 @@ def gen_dynamic_preprocess():
     torch.save(out, OUT / "dynamic_preprocess.pt")
 
 
+def gen_extract_media():
+    """reference extract_media (llava/utils/media.py) on the seeded prompt shapes of
+    validate_against_reference.extract_media_cases() -> tests/golden/extract_media.json"""
+    import json
+    import tempfile
+    ns, media_mod = V.ref_extract_media_namespace()
+    cfg = types.SimpleNamespace(num_video_frames=8, fps=0.0)
+    out = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for label, spec in V.extract_media_cases(tmp):
+            parts = V.build_prompt_parts(spec, tmp, media_mod.Image, media_mod.Video)
+            conv = [{"from": "human", "value": parts if len(parts) > 1 or not isinstance(parts[0], str) else parts[0]}]
+            media = ns["extract_media"](conv, cfg)
+            out.append({"label": label, "spec": spec, "text": conv[0]["value"], "stripped": conv[0]["value"].strip(),
+                        "image_sizes": [list(im.size) for im in media["image"]]})
+    (OUT / "extract_media.json").write_text(json.dumps(out, indent=1))
+
+
 def gen_api_signatures():
     """Public-method signatures of the reference's model classes, extracted from the source with ast
     (names, order, literal defaults, *args / **kwargs) -> tests/golden/api_signatures.json."""
@@ -280,6 +298,6 @@ if __name__ == "__main__":
     torch.set_num_threads(4)
     if "--new-only" not in sys.argv:
         gen_siglip(); gen_projector(); gen_arch_glue(); gen_qwen2(); gen_media()
-    gen_packing(); gen_dynamic_preprocess(); gen_api_signatures()
+    gen_packing(); gen_dynamic_preprocess(); gen_extract_media(); gen_api_signatures()
     for f in sorted(OUT.glob("*.pt")):
         print(f.name, f.stat().st_size)

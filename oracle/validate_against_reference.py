@@ -407,6 +407,98 @@ def check_dynamic_preprocess():
     report("dynamic_preprocess / expand2square pixels", worst, 0)
 
 
+def extract_media_cases(tmp_dir):
+    """Seeded prompts for the prompt-flattening check: (label, spec) with spec a list of
+    ("text", str) | ("pil", w, h, seed) | ("image_file", w, h, seed) | ("video_dir", n_frames).
+    `build_prompt_parts` turns a spec into real prompt parts for either implementation."""
+    return [
+        ("plain string", [("text", "What is the capital of France?")]),
+        ("text image text", [("text", "look: "), ("pil", 64, 48, 1), ("text", "what?")]),
+        ("two images", [("pil", 32, 32, 2), ("pil", 40, 24, 3), ("text", "compare")]),
+        ("stray media token in the text", [("text", "<image> a token typed by hand "), ("pil", 32, 32, 4)]),
+        ("stray video token, whitespace", [("text", "  before <vila/video> after  "), ("pil", 16, 16, 5), ("text", "\nnew line")]),
+        ("image file", [("image_file", 48, 32, 6), ("text", "from a path")]),
+        ("video directory (5 frames -> 8)", [("video_dir", 5), ("text", "describe the video")]),
+        ("video then image", [("video_dir", 3), ("pil", 20, 20, 7), ("text", "q")]),
+    ]
+
+
+def build_prompt_parts(spec, tmp_dir, ImageCls, VideoCls):
+    import numpy as np
+    from PIL import Image as PILImage
+    from pathlib import Path as _P
+    parts = []
+    for i, item in enumerate(spec):
+        if item[0] == "text":
+            parts.append(item[1])
+        elif item[0] in ("pil", "image_file"):
+            _, w, h, seed = item
+            img = PILImage.fromarray(np.random.RandomState(seed).randint(0, 256, (h, w, 3), dtype=np.uint8))
+            if item[0] == "pil":
+                parts.append(img)
+            else:
+                f = _P(tmp_dir) / f"img_{seed}.png"
+                img.save(f)
+                parts.append(ImageCls(str(f)))
+        else:
+            d = _P(tmp_dir) / f"video_{item[1]}_{i}"
+            d.mkdir(parents=True, exist_ok=True)
+            for k in range(item[1]):
+                PILImage.fromarray(np.full((24, 32, 3), 10 * k, dtype=np.uint8)).save(d / f"frame_{k:03d}.png")
+            parts.append(VideoCls(str(d)))
+    return parts
+
+
+def ref_extract_media_namespace():
+    """llava/utils/media.py functions executed from the reference source (its module imports cv2 /
+    requests / llava.* at the top, so the functions are lifted out with ast)."""
+    import glob
+    import os
+    from collections import defaultdict
+    from typing import Any, Dict, List, Optional, Union
+    import numpy as np
+    import PIL.Image
+    media_mod = load_by_path("ref_llava_media", REF / "llava/media.py")
+    srcs = extract_functions(REF / "llava/utils/media.py", ["_extract_image", "_load_video", "_extract_video", "extract_media"])
+    ns = {"glob": glob, "os": os, "np": np, "PIL": PIL, "defaultdict": defaultdict, "Any": Any, "Dict": Dict,
+          "List": List, "Optional": Optional, "Union": Union, "PretrainedConfig": object,
+          "Image": media_mod.Image, "Video": media_mod.Video,
+          "MEDIA_TOKENS": {"image": "<image>", "video": "<vila/video>"},
+          "make_list": lambda x: x if isinstance(x, list) else [x],
+          "logger": types.SimpleNamespace(warning=lambda *a, **k: None, info=lambda *a, **k: None)}
+    for k in ("_extract_image", "_load_video", "_extract_video", "extract_media"):
+        exec(srcs[k], ns)
+    return ns, media_mod
+
+
+def check_extract_media():
+    """llava/utils/media.py extract_media (+ the .strip() of tokenizer.py:80-82) vs
+    vila_b200.model.media.extract_media: flattened text and the image list."""
+    import tempfile
+    import numpy as np
+    from vila_b200.model import media
+    ns, media_mod = ref_extract_media_namespace()
+    # the constants the namespace hard-codes are the reference's
+    const_src = (REF / "llava/constants.py").read_text()
+    assert '"image": "<image>"' in const_src and '"video": "<vila/video>"' in const_src
+    cfg = types.SimpleNamespace(num_video_frames=8, fps=0.0)
+    bad = 0
+    with tempfile.TemporaryDirectory() as tmp:
+        for label, spec in extract_media_cases(tmp):
+            ref_parts = build_prompt_parts(spec, tmp, media_mod.Image, media_mod.Video)
+            my_parts = build_prompt_parts(spec, tmp, media.Image, media.Video)
+            conv = [{"from": "human", "value": ref_parts if len(ref_parts) > 1 or not isinstance(ref_parts[0], str) else ref_parts[0]}]
+            ref_media = ns["extract_media"](conv, cfg)
+            ref_text, ref_imgs = conv[0]["value"], ref_media["image"]
+            my_text, my_imgs = media.extract_media(my_parts if len(my_parts) > 1 or not isinstance(my_parts[0], str) else my_parts[0], cfg)
+            same = (ref_text == my_text and len(ref_imgs) == len(my_imgs) and all(
+                np.array_equal(np.asarray(a.convert("RGB")), np.asarray(b.convert("RGB"))) for a, b in zip(ref_imgs, my_imgs)))
+            if not same:
+                print("   mismatch:", label, repr(ref_text), repr(my_text), len(ref_imgs), len(my_imgs))
+                bad += 1
+    report("extract_media text + image list (8 prompt shapes)", float(bad), 0)
+
+
 if __name__ == "__main__":
     if not REF.exists():
         print("reference tree not present: nothing to validate against")
@@ -420,6 +512,7 @@ if __name__ == "__main__":
     check_encoders()
     check_packing()
     check_dynamic_preprocess()
+    check_extract_media()
     check_qwen2()
     print("FAILED:" if FAILED else "ALL OK", FAILED)
     sys.exit(1 if FAILED else 0)

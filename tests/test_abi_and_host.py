@@ -94,7 +94,7 @@ def test_dynamic_s2_preprocess_block_sizes():
     assert block_sizes == [bs] and tensors[0].shape == (3, 448, 448)
     assert abs(float(tensors[0][0].mean()) - (120 / 255 - 0.5) / 0.5) < 1e-2
     text, images = media.extract_media(["look: ", img, "what?"], cfg)
-    assert text == "look: <image>\nwhat?" and len(images) == 1
+    assert text == "look: <image>what?" and len(images) == 1  # bare token: the "\n" is the encoder's end token
 
 
 def test_dynamic_s2_preprocess_matches_reference_fixture():

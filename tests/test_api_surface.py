@@ -235,3 +235,33 @@ def test_chat_completions_server_plumbing():
     assert json.loads(chunks[0][6:])["choices"][0]["delta"]["content"] == "he"
     with pytest.raises(ValueError):
         asyncio.run(S.Engine(Stub(), "other").complete(req()))
+
+
+def test_extract_media_matches_reference_fixture(tmp_path):
+    """Prompt flattening (llava/utils/media.py:93-123 + the strip of utils/tokenizer.py:80-82): the text
+    the tokenizer sees and the image list, against outputs of the reference's own function
+    (tests/golden/extract_media.json, oracle/gen_golden.py)."""
+    import json
+    from types import SimpleNamespace
+    from oracle.validate_against_reference import build_prompt_parts
+    from vila_b200.model import media
+    cases = json.loads((GOLDEN / "extract_media.json").read_text())
+    assert len(cases) >= 8
+    cfg = SimpleNamespace(num_video_frames=8, fps=0.0)
+    for c in cases:
+        spec = [tuple(x) for x in c["spec"]]
+        parts = build_prompt_parts(spec, tmp_path, media.Image, media.Video)
+        prompt = parts if len(parts) > 1 or not isinstance(parts[0], str) else parts[0]
+        text, images = media.extract_media(prompt, cfg)
+        assert text == c["text"], c["label"]
+        assert [list(im.size) for im in images] == c["image_sizes"], c["label"]
+
+        class Tok:  # records what reaches the tokenizer
+            def __call__(self, t):
+                self.seen = t
+                return SimpleNamespace(input_ids=[1])
+        tok = Tok()
+        media.tokenize_conversation(text, tok)
+        assert tok.seen == c["stripped"], c["label"]
+    with pytest.raises(ValueError):
+        media.extract_media(["x", 3.14], cfg)

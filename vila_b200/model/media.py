@@ -20,6 +20,7 @@ import torch
 from .configuration import LlavaConfig
 
 DEFAULT_IMAGE_TOKEN = "<image>"
+MEDIA_TOKENS = {"image": "<image>", "video": "<vila/video>"}   # llava/constants.py:32-35
 SIGLIP_MEAN = 0.5  # SiglipImageProcessor: rescale 1/255, normalise mean=std=0.5, bicubic resize
 SIGLIP_STD = 0.5
 
@@ -41,9 +42,10 @@ class Video(File):
     pass
 
 
-def load_video_frames(path: str, num_frames: int) -> list:
-    """llava/utils/media.py:_load_video: a directory of frame images or a video file (cv2), sampled
-    uniformly to num_frames PIL images."""
+def load_video_frames(path: str, num_frames: int, fps: float = 0.0) -> list:
+    """llava/utils/media.py:40-85 `_load_video`: a directory of frame images or a video file (cv2).
+    fps <= 0: num_frames indices spread uniformly over the clip; fps > 0: one frame every 1/fps
+    seconds, at most num_frames.  Frames that fail to decode are skipped, duplicates decoded once."""
     import glob
     import os
 
@@ -55,40 +57,62 @@ def load_video_frames(path: str, num_frames: int) -> list:
         return [PIL.Image.open(paths[i]) for i in idx]
     import cv2
     cap = cv2.VideoCapture(path)
+    video_fps = cap.get(cv2.CAP_PROP_FPS)
+    # the container's frame count can overshoot: walk back to the last frame that can be grabbed
     count = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    while count > 0:
+        cap.set(cv2.CAP_PROP_POS_FRAMES, count - 1)
+        if cap.grab():
+            break
+        count -= 1
     if count <= 0:
         raise ValueError(f"Video '{path}' has no frames.")
+    if fps > 0:
+        duration = count / video_fps if video_fps > 0 else 0
+        stamps = np.arange(0, duration, 1.0 / fps)[:num_frames]
+        indices = [int(t * video_fps) for t in stamps]
+    else:
+        indices = [int(i) for i in np.round(np.linspace(0, count - 1, num_frames)).astype(int)]
     frames = {}
-    for i in np.round(np.linspace(0, count - 1, num_frames)).astype(int):
-        if int(i) in frames:
+    for i in indices:
+        if i in frames:
             continue
-        cap.set(cv2.CAP_PROP_POS_FRAMES, int(i))
+        cap.set(cv2.CAP_PROP_POS_FRAMES, i)
         ok, frame = cap.read()
         if ok:
-            frames[int(i)] = PIL.Image.fromarray(cv2.cvtColor(frame, cv2.COLOR_BGR2RGB))
-    return [frames[k] for k in sorted(frames)]
+            frames[i] = PIL.Image.fromarray(cv2.cvtColor(frame, cv2.COLOR_BGR2RGB))
+    return [frames[i] for i in indices if i in frames]
 
 
 def extract_media(prompt: Union[str, list], config: LlavaConfig):
     """Flatten a prompt (str | list of str / PIL images / image tensors / llava.Image / llava.Video)
-    into text with <image> tokens + the image list (llava/utils/media.py:93-123: a video becomes
-    `num_video_frames` images)."""
-    if isinstance(prompt, str):
-        return prompt, []
+    into (text, images) the way llava/utils/media.py:93-123 does: media tokens typed into a text part
+    are removed (and that part stripped), every image contributes one bare `<image>`, a video
+    contributes `num_video_frames` of them and its frames join the image list.  (The "\n" after an
+    image is not text: it is the image encoder's end token, encoders/image/basic.py.)"""
+    import PIL.Image
+    parts = list(prompt) if isinstance(prompt, (list, tuple)) else [prompt]
     text, images = "", []
-    for part in prompt:
+    for part in parts:
         if isinstance(part, str):
+            for token in MEDIA_TOKENS.values():
+                if token in part:
+                    part = part.replace(token, "").strip()
             text += part
         elif isinstance(part, Video):
-            frames = load_video_frames(part.path, config.num_video_frames)
-            images.extend(frames)
-            text += (DEFAULT_IMAGE_TOKEN + "\n") * len(frames)
-        else:
+            images.extend(load_video_frames(part.path, config.num_video_frames, getattr(config, "fps", 0.0)))
+            text += DEFAULT_IMAGE_TOKEN * config.num_video_frames
+        elif isinstance(part, (Image, PIL.Image.Image, torch.Tensor)):
             if isinstance(part, Image):
-                import PIL.Image
-                part = PIL.Image.open(part.path)
+                if part.path.startswith(("http://", "https://")):
+                    import requests
+                    part = PIL.Image.open(requests.get(part.path, stream=True).raw)
+                else:
+                    part = PIL.Image.open(part.path)
             images.append(part)
-            text += DEFAULT_IMAGE_TOKEN + "\n"
+            text += DEFAULT_IMAGE_TOKEN
+        else:
+            raise ValueError(f"Unsupported prompt part type: {type(part)}")
     return text, images
 
 
@@ -227,6 +251,7 @@ def dynamic_prompt(text: str, n_tiles: int) -> str:
 def tokenize_conversation(text: str, tokenizer) -> List[int]:
     """Single human turn + generation prompt. With a real HF tokenizer the chat template is used and
     media tokens are mapped to their ids; the synthetic tokenizer handles both directly."""
+    text = text.strip()  # llava/utils/tokenizer.py:80-82 normalises every message before the template
     if hasattr(tokenizer, "apply_chat_template"):
         rendered = tokenizer.apply_chat_template([{"role": "user", "content": text}],
                                                  add_generation_prompt=True, tokenize=False)
