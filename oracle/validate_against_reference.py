@@ -499,6 +499,35 @@ def check_extract_media():
     report("extract_media text + image list (8 prompt shapes)", float(bad), 0)
 
 
+def check_server_video_sampling():
+    """serving/server.py sample_frames_from_video (int(total / n * i), its own rule) executed from the
+    reference source vs vila_b200.server on a synthetic 23-frame mp4 sent as a base64 data URL."""
+    import base64
+    import os
+    import tempfile
+    import cv2
+    import numpy as np
+    from PIL import Image as PILImage
+    from vila_b200 import server
+    srcs = extract_functions(REF / "serving/server.py", ["sample_frames_from_video"])
+    ns = {"cv2": cv2, "PILImage": PILImage}
+    exec(srcs["sample_frames_from_video"], ns)
+    bad = 0
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "clip.mp4")
+        wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 10, (64, 48))
+        for k in range(23):
+            wr.write(np.full((48, 64, 3), k * 10, dtype=np.uint8))
+        wr.release()
+        url = "data:video/mp4;base64," + base64.b64encode(open(path, "rb").read()).decode()
+        for n in (8, 5, 16):
+            ref = ns["sample_frames_from_video"](path, n)
+            mine = server.sample_frames_from_video(server.load_video(url), n)
+            if len(ref) != len(mine) or not all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(ref, mine)):
+                bad += 1
+    report("server video_url frame sampling (3 frame counts)", float(bad), 0)
+
+
 if __name__ == "__main__":
     if not REF.exists():
         print("reference tree not present: nothing to validate against")
@@ -513,6 +542,7 @@ if __name__ == "__main__":
     check_packing()
     check_dynamic_preprocess()
     check_extract_media()
+    check_server_video_sampling()
     check_qwen2()
     print("FAILED:" if FAILED else "ALL OK", FAILED)
     sys.exit(1 if FAILED else 0)

@@ -265,3 +265,27 @@ def test_extract_media_matches_reference_fixture(tmp_path):
         assert tok.seen == c["stripped"], c["label"]
     with pytest.raises(ValueError):
         media.extract_media(["x", 3.14], cfg)
+
+
+def test_server_video_url_sampling(tmp_path):
+    """`video_url` parts (serving/server.py:106-143,246-252): a base64 mp4 becomes `frames` PIL images taken at
+    index int(total / frames * i) — the server's rule, not extract_media's linspace (validated against the
+    reference function in oracle/validate_against_reference.py)."""
+    import base64
+    cv2 = pytest.importorskip("cv2")
+    from vila_b200 import server
+    path = str(tmp_path / "clip.mp4")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 10, (64, 48))
+    for k in range(23):
+        wr.write(np.full((48, 64, 3), k * 10, dtype=np.uint8))
+    wr.release()
+    url = "data:video/mp4;base64," + base64.b64encode(open(path, "rb").read()).decode()
+    msg = server.ChatMessage(role="user", content=[
+        {"type": "video_url", "video_url": {"url": url}, "frames": 8}, {"type": "text", "text": "what happens?"}])
+    prompt = server.build_prompt([msg])
+    assert len(prompt) == 9 and prompt[-1] == "what happens?"
+    got = [int(np.asarray(f)[0, 0, 0]) for f in prompt[:8]]
+    want = [10 * int(23 / 8 * i) for i in range(8)]
+    assert all(abs(g - w) <= 8 for g, w in zip(got, want)), (got, want)   # mp4v is lossy by a few levels
+    with pytest.raises(ValueError):
+        server.load_video("data:video/avi;base64,AAAA")

@@ -24,6 +24,7 @@ from typing import Any, Dict, List, Literal, Optional, Union
 from pydantic import BaseModel
 
 IMAGE_B64 = re.compile(r"^data:image/(png|jpe?g);base64,(.*)$")
+VIDEO_B64 = re.compile(r"^data:video/(mp4);base64,(.*)$")
 
 
 class MediaURL(BaseModel):
@@ -73,9 +74,51 @@ def load_image(url: str):
     return Image.open(BytesIO(base64.b64decode(m.groups()[1]))).convert("RGB")
 
 
+def load_video(url: str) -> str:
+    """A `video_url` -> a file on disk (serving/server.py:124-143: base64 mp4 data URL or http(s)
+    download).  A path that exists locally is accepted as it is (no network on a serving box)."""
+    import os
+    import tempfile
+    if url.startswith("http"):
+        import requests
+        payload = requests.get(url).content
+    else:
+        m = VIDEO_B64.match(url)
+        if m is None:
+            if os.path.exists(url):
+                return url
+            raise ValueError(f"Invalid video url: {url[:64]}")
+        payload = base64.b64decode(m.groups()[1])
+    path = os.path.join(tempfile.mkdtemp(prefix="vila_serving_"), f"{uuid.uuid5(uuid.NAMESPACE_DNS, url)}.mp4")
+    with open(path, "wb") as f:
+        f.write(payload)
+    return path
+
+
+def sample_frames_from_video(path: str, num_frames: int = 8) -> list:
+    """The server's own sampling rule (serving/server.py:106-122), not `_load_video`'s: frame i of n sits at
+    index int(total / n * i); unreadable frames are dropped; a directory of frames is sampled the same way."""
+    import os
+    from PIL import Image
+    if os.path.isdir(path):
+        files = sorted(os.path.join(path, f) for f in os.listdir(path))
+        return [Image.open(files[int(len(files) / num_frames * i)]).convert("RGB") for i in range(num_frames)]
+    import cv2
+    cap = cv2.VideoCapture(path)
+    total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    frames = []
+    for i in range(num_frames):
+        cap.set(cv2.CAP_PROP_POS_FRAMES, int(total / num_frames * i))
+        ok, frame = cap.read()
+        if ok:
+            frames.append(Image.fromarray(cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)))
+    cap.release()
+    return frames
+
+
 def build_prompt(messages: List[ChatMessage], num_video_frames: int = 8) -> list:
-    """messages -> the prompt list generate_content takes (server.py:236-256)."""
-    from .model.media import Video, load_video_frames
+    """messages -> the prompt list generate_content takes (serving/server.py:234-256): strings and text
+    parts as they come, images decoded to PIL, a video replaced by its sampled frames (as images)."""
     prompt: list = []
     for message in messages:
         if isinstance(message.content, str):
@@ -87,7 +130,7 @@ def build_prompt(messages: List[ChatMessage], num_video_frames: int = 8) -> list
             elif part.type == "image_url":
                 prompt.append(load_image(part.image_url.url))
             elif part.type == "video_url":
-                prompt += load_video_frames(part.video_url.url, part.frames or num_video_frames)
+                prompt += sample_frames_from_video(load_video(part.video_url.url), part.frames or num_video_frames)
             else:
                 raise NotImplementedError(f"Unsupported content type: {part.type}")
     return prompt
