@@ -407,6 +407,70 @@ def check_dynamic_preprocess():
     report("dynamic_preprocess / expand2square pixels", worst, 0)
 
 
+def check_process_image_branches():
+    """mm_utils.process_image / process_images (:442-541) executed from the reference source, with a
+    PIL-backed stand-in for the 4.46 SiglipImageProcessor (its pixel step is pinned separately in
+    check_pixel_preprocess), vs vila_b200.model.media.process_image(s): every aspect-ratio branch
+    (`resize`, `pad`, `dynamic`, `dynamic_s2`, default) must produce the same tensors / block sizes."""
+    import os
+    import numpy as np
+    from PIL import Image
+    from vila_b200.model import LlavaConfig, media
+    names = ["find_closest_aspect_ratio", "dynamic_preprocess", "dynamic_s2_preprocess", "process_image", "process_images"]
+    srcs = extract_functions(REF / "llava/mm_utils.py", names)
+    ns = {"Image": Image, "os": os, "torch": torch}
+    for k in names:
+        exec(srcs[k], ns)
+
+    class Processor:  # SigLIP flavour: `size`, no `crop_size`
+        size = {"height": 448, "width": 448}
+        image_mean = [0.5, 0.5, 0.5]
+
+        def preprocess(self, image, return_tensors="pt"):
+            return {"pixel_values": [media._to_tensor(image, 448)]}
+
+    rng = np.random.RandomState(21)
+    sizes = [(448, 448), (640, 480), (333, 1000), (1600, 800), (97, 131)]
+    worst, bad = 0.0, 0
+    for mode in ("resize", "pad", "dynamic", "dynamic_s2", "default"):
+        ref_args = types.SimpleNamespace(image_processor=Processor(), image_aspect_ratio=mode, s2_scales=[448, 896, 1344],
+                                         max_tiles=12, min_tiles=1)
+        cfg = LlavaConfig(image_aspect_ratio=mode, dynamic_s2=(mode == "dynamic_s2"))
+        for (w, h) in sizes:
+            img = Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8))
+            if mode == "dynamic_s2":
+                ref, ref_bs = ns["process_image"](img, ref_args, None, enable_dynamic_s2=True)
+                mine, my_bs = media.process_image(img, cfg, enable_dynamic_s2=True)
+                bad += int(tuple(ref_bs) != tuple(my_bs))
+            elif mode == "dynamic":
+                for mt in (None, 6):
+                    ref = ns["process_image"](img, ref_args, None, enable_dynamic_res=True, max_tiles=mt)
+                    mine = media.process_image(img, cfg, enable_dynamic_res=True, max_tiles=mt)
+                    if ref.shape != mine.shape:
+                        bad += 1
+                    else:
+                        worst = max(worst, float((ref - mine).abs().max()))
+                continue
+            else:
+                ref = ns["process_image"](img, ref_args, None)
+                mine = media.process_image(img, cfg)
+            if ref.shape != mine.shape:
+                bad += 1
+            else:
+                worst = max(worst, float((ref - mine).abs().max()))
+        # process_images: a list of images -> one stacked batch (the multi-image / video-frame path)
+        imgs = [Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8)) for (w, h) in sizes[:3]]
+        if mode in ("resize", "pad", "default"):
+            ref_b = ns["process_images"](imgs, Processor(), ref_args)
+            mine_b, _ = media.process_images(imgs, cfg)
+            if tuple(ref_b.shape) != (len(mine_b),) + tuple(mine_b[0].shape):
+                bad += 1
+            else:
+                worst = max(worst, float((ref_b - torch.stack(mine_b)).abs().max()))
+    report("process_image(s): shapes / block sizes over 5 aspect-ratio branches", float(bad), 0)
+    report("process_image(s): tensors over 5 aspect-ratio branches", worst, 0)
+
+
 def extract_media_cases(tmp_dir):
     """Seeded prompts for the prompt-flattening check: (label, spec) with spec a list of
     ("text", str) | ("pil", w, h, seed) | ("image_file", w, h, seed) | ("video_dir", n_frames).
@@ -541,6 +605,7 @@ if __name__ == "__main__":
     check_encoders()
     check_packing()
     check_dynamic_preprocess()
+    check_process_image_branches()
     check_extract_media()
     check_server_video_sampling()
     check_qwen2()
