@@ -251,6 +251,24 @@ def gen_extract_media():
     (OUT / "extract_media.json").write_text(json.dumps(out, indent=1))
 
 
+def gen_tokenizer_setup():
+    """reference infer_stop_tokens / media-token registration / tokenize_conversation on the in-memory
+    HF tokenizer of validate_against_reference.toy_chat_tokenizer() -> tests/golden/tokenizer_setup.json"""
+    import json
+    ns = V.ref_tokenizer_namespace()
+    tok = V.toy_chat_tokenizer()
+    stop = ns["infer_stop_tokens"](tok)
+    media = {}
+    for name, token in {"image": "<image>", "video": "<vila/video>"}.items():
+        tok.add_tokens([token], special_tokens=True)
+        media[name] = tok.convert_tokens_to_ids(token)
+    prompts = ["Describe the image .", "<image>Describe the image .", "look : <image>what ?", "  <image><image>compare  "]
+    ids = [ns["tokenize_conversation"]([{"from": "human", "value": t}], tok, add_generation_prompt=True).tolist() for t in prompts]
+    (OUT / "tokenizer_setup.json").write_text(json.dumps({
+        "stop_tokens": sorted(stop), "stop_token_ids": sorted(tok.convert_tokens_to_ids(stop)), "media_token_ids": media,
+        "sentinel_token_id": tok.sentinel_token_id, "prompts": prompts, "input_ids": ids}, indent=1))
+
+
 def gen_api_signatures():
     """Public-method signatures of the reference's model classes, extracted from the source with ast
     (names, order, literal defaults, *args / **kwargs) -> tests/golden/api_signatures.json."""
@@ -298,6 +316,6 @@ if __name__ == "__main__":
     torch.set_num_threads(4)
     if "--new-only" not in sys.argv:
         gen_siglip(); gen_projector(); gen_arch_glue(); gen_qwen2(); gen_media()
-    gen_packing(); gen_dynamic_preprocess(); gen_extract_media(); gen_api_signatures()
+    gen_packing(); gen_dynamic_preprocess(); gen_extract_media(); gen_tokenizer_setup(); gen_api_signatures()
     for f in sorted(OUT.glob("*.pt")):
         print(f.name, f.stat().st_size)

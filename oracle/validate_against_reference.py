@@ -471,6 +471,71 @@ def check_process_image_branches():
     report("process_image(s): tensors over 5 aspect-ratio branches", worst, 0)
 
 
+def toy_chat_tokenizer():
+    """A genuine HF fast tokenizer (word-level vocabulary, ChatML-style template like Qwen2's) built in
+    memory: no tokenizer files ship with the image, but apply_chat_template / add_tokens / decode are
+    the real transformers code paths."""
+    from tokenizers import Regex, Tokenizer, models, pre_tokenizers
+    from transformers import PreTrainedTokenizerFast
+    words = ["<unk>", "<|im_start|>", "<|im_end|>", "<|endoftext|>", "\n", "system", "user", "assistant", "question",
+             "answer", "You", "are", "a", "helpful", "Describe", "the", "image", ".", "what", "?", "look", ":", "compare"]
+    t = Tokenizer(models.WordLevel({w: i for i, w in enumerate(words)}, unk_token="<unk>"))
+    t.pre_tokenizer = pre_tokenizers.Sequence([pre_tokenizers.Split("\n", "isolated"),
+                                               pre_tokenizers.Split(Regex(" +"), "removed")])
+    tok = PreTrainedTokenizerFast(tokenizer_object=t, unk_token="<unk>", eos_token="<|endoftext|>",
+                                  pad_token="<|endoftext|>", additional_special_tokens=["<|im_start|>", "<|im_end|>"])
+    tok.chat_template = ("{% for message in messages %}{{'<|im_start|>' + message['role'] + '\n' + message['content'] + "
+                         "'<|im_end|>' + '\n'}}{% endfor %}{% if add_generation_prompt %}{{ '<|im_start|>assistant\n' }}{% endif %}")
+    return tok
+
+
+def ref_tokenizer_namespace():
+    """llava/utils/tokenizer.py functions lifted out of the reference source (the module imports
+    llava.conversation / llava.mm_utils at the top): tokenize_conversation, infer_stop_tokens."""
+    from typing import Any, Dict, List, Optional, Sequence
+    import transformers
+    names = ["tokenize_conversation", "_maybe_add_sentinel_token", "infer_stop_tokens"]
+    srcs = extract_functions(REF / "llava/utils/tokenizer.py", names)
+    mm = extract_functions(REF / "llava/mm_utils.py", ["tokenizer_image_token"])
+    auto = types.SimpleNamespace(AUTO="auto")
+    ns = {"torch": torch, "transformers": transformers, "Any": Any, "Dict": Dict, "List": List, "Optional": Optional,
+          "Sequence": Sequence, "SENTINEL_TOKEN": "<vila/sentinel>", "IGNORE_INDEX": -100,
+          "conversation_lib": types.SimpleNamespace(SeparatorStyle=auto, default_conversation=types.SimpleNamespace(sep_style="auto")),
+          "DUMMY_CONVERSATION": [{"from": "human", "value": "question"}, {"from": "gpt", "value": "answer"}] * 10}
+    exec(mm["tokenizer_image_token"], ns)
+    for k in names:
+        exec(srcs[k], ns)
+    return ns
+
+
+def check_tokenizer_setup():
+    """build_llm_and_tokenizer's tokenizer preparation (builder.py:187-211) + utils/tokenizer.py
+    (infer_stop_tokens, tokenize_conversation with add_generation_prompt) executed from the reference
+    source on a real HF tokenizer, vs vila_b200.model.loading.prepare_tokenizer and
+    media.tokenize_conversation: stop tokens, media token ids, prompt ids."""
+    import copy
+    from vila_b200.model import loading, media
+    ns = ref_tokenizer_namespace()
+    ref_tok, my_tok = toy_chat_tokenizer(), toy_chat_tokenizer()
+    # reference order: stop tokens (adds the sentinel), then the media tokens
+    ref_tok.stop_tokens = ns["infer_stop_tokens"](ref_tok)
+    ref_tok.stop_token_ids = ref_tok.convert_tokens_to_ids(ref_tok.stop_tokens)
+    ref_media = {}
+    for name, token in {"image": "<image>", "video": "<vila/video>"}.items():
+        ref_tok.add_tokens([token], special_tokens=True)
+        ref_media[name] = ref_tok.convert_tokens_to_ids(token)
+    loading.prepare_tokenizer(my_tok, model_max_length=4096)
+    bad = int(sorted(ref_tok.stop_tokens) != sorted(my_tok.stop_tokens)) + int(ref_media != my_tok.media_token_ids) \
+        + int(sorted(ref_tok.stop_token_ids) != sorted(my_tok.stop_token_ids))
+    report("tokenizer setup: stop tokens + media token ids", float(bad), 0)
+    bad = 0
+    for text in ("Describe the image .", "<image>Describe the image .", "look : <image>what ?", "  <image><image>compare  "):
+        ref_ids = ns["tokenize_conversation"]([{"from": "human", "value": text}], ref_tok, add_generation_prompt=True)
+        mine = media.tokenize_conversation(text, my_tok)
+        bad += int(ref_ids.tolist() != list(mine))
+    report("tokenize_conversation ids (4 prompts, generation prompt appended)", float(bad), 0)
+
+
 def extract_media_cases(tmp_dir):
     """Seeded prompts for the prompt-flattening check: (label, spec) with spec a list of
     ("text", str) | ("pil", w, h, seed) | ("image_file", w, h, seed) | ("video_dir", n_frames).
@@ -607,6 +672,7 @@ if __name__ == "__main__":
     check_dynamic_preprocess()
     check_process_image_branches()
     check_extract_media()
+    check_tokenizer_setup()
     check_server_video_sampling()
     check_qwen2()
     print("FAILED:" if FAILED else "ALL OK", FAILED)

@@ -289,3 +289,22 @@ def test_server_video_url_sampling(tmp_path):
     assert all(abs(g - w) <= 8 for g, w in zip(got, want)), (got, want)   # mp4v is lossy by a few levels
     with pytest.raises(ValueError):
         server.load_video("data:video/avi;base64,AAAA")
+
+
+def test_tokenizer_setup_matches_reference_fixture():
+    """What the reference does to the HF tokenizer at load (builder.py:187-211: stop tokens inferred from the
+    chat template, media tokens registered) and `tokenize_conversation(..., add_generation_prompt=True)`,
+    on a real (in-memory) HF tokenizer — against values produced by the reference's own functions."""
+    pytest.importorskip("tokenizers")
+    from oracle.validate_against_reference import toy_chat_tokenizer
+    from vila_b200.model import loading, media
+    want = json.loads((GOLDEN / "tokenizer_setup.json").read_text())
+    tok = loading.prepare_tokenizer(toy_chat_tokenizer(), model_max_length=4096)
+    assert tok.padding_side == "right" and tok.model_max_length == 4096
+    assert sorted(tok.stop_tokens) == want["stop_tokens"] and sorted(tok.stop_token_ids) == want["stop_token_ids"]
+    assert tok.media_token_ids == want["media_token_ids"] and tok.sentinel_token_id == want["sentinel_token_id"]
+    for text, ids in zip(want["prompts"], want["input_ids"]):
+        assert list(media.tokenize_conversation(text, tok)) == ids, text
+    # idempotent: a tokenizer that already carries the tokens (a saved NVILA checkpoint) keeps its ids
+    again = loading.prepare_tokenizer(tok)
+    assert again.media_token_ids == want["media_token_ids"]

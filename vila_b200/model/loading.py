@@ -21,6 +21,50 @@ from .configuration import LlavaConfig, Qwen2Config, SiglipVisionConfig
 from .llava_llama import LlavaLlamaModel
 
 
+SENTINEL_TOKEN = "<vila/sentinel>"     # llava/constants.py
+MEDIA_TOKENS = {"image": "<image>", "video": "<vila/video>"}
+
+
+def infer_stop_tokens(tok) -> list:
+    """llava/utils/tokenizer.py:174-183: the stop tokens are the EOS token plus whatever the chat
+    template puts right after an assistant turn — found by rendering a dummy conversation whose
+    answers are a sentinel token and reading the token that follows each sentinel."""
+    if not hasattr(tok, "sentinel_token"):
+        tok.add_tokens([SENTINEL_TOKEN], special_tokens=True)
+        tok.sentinel_token = SENTINEL_TOKEN
+        tok.sentinel_token_id = tok.convert_tokens_to_ids(SENTINEL_TOKEN)
+    turns = []
+    for _ in range(10):
+        turns += [{"role": "user", "content": "question"}, {"role": "assistant", "content": SENTINEL_TOKEN}]
+    ids = tok(tok.apply_chat_template(turns, add_generation_prompt=False, tokenize=False)).input_ids
+    stops = {tok.eos_token}
+    for here, nxt in zip(ids[:-1], ids[1:]):
+        if here == tok.sentinel_token_id:
+            stops.add(tok.decode(nxt))
+    return list(stops)
+
+
+def prepare_tokenizer(tok, model_max_length=None, chat_template: str = None):
+    """What build_llm_and_tokenizer does to the HF tokenizer after loading it
+    (llava/model/language_model/builder.py:187-211): right padding, the model's context length, an
+    optional chat template, `stop_tokens` / `stop_token_ids`, and the media tokens registered as
+    special tokens with their ids in `media_token_ids` (sentinel first, then <image>, <vila/video> —
+    the order fixes the ids of tokens a tokenizer does not have yet)."""
+    tok.padding_side = "right"
+    if model_max_length is not None:
+        tok.model_max_length = model_max_length
+    if chat_template is not None:
+        tok.chat_template = chat_template.replace("    ", "").replace("\n", "")
+    tok.stop_tokens = infer_stop_tokens(tok)
+    tok.stop_token_ids = tok.convert_tokens_to_ids(tok.stop_tokens)
+    tok.media_tokens = dict(MEDIA_TOKENS)
+    tok.media_token_ids = {}
+    for name, token in MEDIA_TOKENS.items():
+        tok.add_tokens([token], special_tokens=True)
+        tok.media_token_ids[name] = tok.convert_tokens_to_ids(token)
+    return tok
+
+
 def _load_dir_tensors(d: Path) -> Dict[str, torch.Tensor]:
     from safetensors.torch import load_file
 
@@ -73,18 +117,16 @@ def load_pretrained(model_path: str, device="cuda", model_cls=None) -> LlavaLlam
     has_tok_files = any((d / "llm" / f).exists() for f in ("tokenizer.json", "vocab.json",
                                                             "tokenizer_config.json"))
     if has_tok_files:  # a real checkpoint ships the tokenizer next to the LLM
-        try:
-            from transformers import AutoTokenizer
-            tok = AutoTokenizer.from_pretrained(str(d / "llm"))
-            ids = {"image": tok.convert_tokens_to_ids("<image>"),
-                   "video": tok.convert_tokens_to_ids("<vila/video>")}
-            if not all(isinstance(v, int) and v >= 0 for v in ids.values()):
-                raise ValueError("media tokens missing from the tokenizer")
-            tok.media_token_ids = ids
-            tok.stop_token_ids = [tok.eos_token_id]
-            cfg.image_token_id, cfg.video_token_id = ids["image"], ids["video"]
-        except Exception:
-            tok = None
+        from transformers import AutoTokenizer
+        tok = AutoTokenizer.from_pretrained(str(d / "llm"), padding_side="right", use_fast=True)
+        prepare_tokenizer(tok, cfg.model_max_length)
+        if max(tok.media_token_ids.values()) >= cfg.llm_cfg.vocab_size:
+            raise ValueError(f"media token ids {tok.media_token_ids} do not fit the LLM's {cfg.llm_cfg.vocab_size} "
+                             "embedding rows")
+        cfg.image_token_id, cfg.video_token_id = tok.media_token_ids["image"], tok.media_token_ids["video"]
+        cfg.eos_token_ids = tuple(tok.stop_token_ids)
+        if tok.pad_token_id is not None:
+            cfg.pad_token_id = tok.pad_token_id
     model = (model_cls or LlavaLlamaModel)(cfg, device=device, tokenizer=tok)
     gc_file = d / "llm" / "generation_config.json"
     if gc_file.exists():  # HF from_pretrained populates model.generation_config from this file
