@@ -236,6 +236,22 @@ def test_chat_completions_server_plumbing():
     with pytest.raises(ValueError):
         asyncio.run(S.Engine(Stub(), "other").complete(req()))
 
+    # a batch that fails answers EVERY request it took with the error (nobody is left waiting on a future)
+    class Broken(Stub):
+        def generate_content(self, prompt, generation_config=None, response_format=None, stream=False):
+            raise RuntimeError("boom-single")
+
+        def generate_batch(self, requests, max_new_tokens=128, slots=8):
+            raise RuntimeError("boom-batch")
+
+    async def failing():
+        eng = S.Engine(Broken(), "m", slots=4)
+        return await asyncio.wait_for(asyncio.gather(*[eng.complete(req()) for _ in range(3)], return_exceptions=True), 10)
+
+    errs = asyncio.run(failing())
+    assert [type(e) for e in errs] == [RuntimeError] * 3
+    assert [str(e) for e in errs] == ["boom-single", "boom-batch", "boom-batch"]
+
 
 def test_extract_media_matches_reference_fixture(tmp_path):
     """Prompt flattening (llava/utils/media.py:93-123 + the strip of utils/tokenizer.py:80-82): the text

@@ -160,10 +160,16 @@ class Engine:
         async with self.lock:
             if not fut.done():  # this task drains the queue for everyone that piled up behind the lock
                 batch, self.pending = self.pending[:self.slots], self.pending[self.slots:]
-                texts = await loop.run_in_executor(None, self._run_batch, [r for r, _ in batch])
-                for (_, f), t in zip(batch, texts):
-                    if not f.done():
-                        f.set_result(t)
+                try:
+                    texts = await loop.run_in_executor(None, self._run_batch, [r for r, _ in batch])
+                except Exception as e:  # every request of the failed batch gets the error, none is left waiting
+                    for _, f in batch:
+                        if not f.done():
+                            f.set_exception(e)
+                else:
+                    for (_, f), t in zip(batch, texts):
+                        if not f.done():
+                            f.set_result(t)
         text = await fut
         return {"id": uuid.uuid4().hex, "object": "chat.completion", "created": int(time.time()),
                 "model": req.model, "index": 0,
