@@ -56,14 +56,7 @@ class VILAForCausalLM(LlavaLlamaModel):
             gc.eos_token_id = self.tokenizer.eos_token_id
         return gc
 
-    def generate_content(self, prompt, generation_config=None, response_format=None, stream: bool = False):
-        """modeling_vila.py:1128-1244: decodes `output_ids[0]` of ITS generate, i.e. prompt + answer
-        ids; media tokens and special tokens are skipped by the tokenizer."""
-        if stream:
-            return self._generate_content_stream(prompt, generation_config, response_format)
-        with torch.inference_mode():
-            input_ids, media, media_config = self._prepare_content(prompt)
-            gc = generation_config or self.default_generation_config
-            output_ids = self.generate(input_ids=input_ids, media=media, media_config=media_config,
-                                       generation_config=gc)
-            return self.tokenizer.decode(output_ids[0], skip_special_tokens=True).strip()
+    # generate_content (modeling_vila.py:1128-1244) is inherited: it is the same code as llava_arch.py:835-948
+    # (media extraction, response_format -> xgrammar logits processor, greedy retry after a sampling failure) and
+    # decodes `output_ids[0]` of THIS class's generate — i.e. prompt + answer ids; media and special tokens are
+    # skipped by the tokenizer.
