@@ -264,7 +264,13 @@ def gen_tokenizer_setup():
         media[name] = tok.convert_tokens_to_ids(token)
     prompts = ["Describe the image .", "<image>Describe the image .", "look : <image>what ?", "  <image><image>compare  "]
     ids = [ns["tokenize_conversation"]([{"from": "human", "value": t}], tok, add_generation_prompt=True).tolist() for t in prompts]
-    (OUT / "tokenizer_setup.json").write_text(json.dumps({
+    import copy
+    convs = [[{"from": "human", "value": " <image>Describe the image . "}, {"from": "gpt", "value": "answer"}],
+             [{"from": "human", "value": "question"}, {"from": "gpt", "value": "answer"}, {"from": "human", "value": "what ?"}]]
+    kwargs = [{}, {"add_generation_prompt": True}, {"overrides": {"gpt": "<vila/sentinel>"}}, {"no_system_prompt": True}]
+    multi = [{"conversation": c, "kwargs": kw,
+              "input_ids": ns["tokenize_conversation"](copy.deepcopy(c), tok, **kw).tolist()} for c in convs for kw in kwargs]
+    (OUT / "tokenizer_setup.json").write_text(json.dumps({"conversations": multi,
         "stop_tokens": sorted(stop), "stop_token_ids": sorted(tok.convert_tokens_to_ids(stop)), "media_token_ids": media,
         "sentinel_token_id": tok.sentinel_token_id, "prompts": prompts, "input_ids": ids}, indent=1))
 

@@ -324,3 +324,34 @@ def test_tokenizer_setup_matches_reference_fixture():
     # idempotent: a tokenizer that already carries the tokens (a saved NVILA checkpoint) keeps its ids
     again = loading.prepare_tokenizer(tok)
     assert again.media_token_ids == want["media_token_ids"]
+
+
+def test_llava_utils_shim_matches_reference_fixture(tmp_path):
+    """`llava.constants`, `llava.utils.media.extract_media(messages, config, draft)` and
+    `llava.utils.tokenizer.tokenize_conversation(messages, tokenizer, add_generation_prompt, overrides,
+    no_system_prompt)` in the reference's call forms, against reference-generated fixtures."""
+    import copy
+    pytest.importorskip("tokenizers")
+    import llava
+    from llava.constants import DEFAULT_IMAGE_TOKEN, IGNORE_INDEX, MEDIA_TOKENS, SENTINEL_TOKEN
+    from llava.utils import make_list
+    from llava.utils.media import extract_media
+    from llava.utils.tokenizer import infer_stop_tokens, tokenize_conversation
+    from oracle.validate_against_reference import build_prompt_parts, toy_chat_tokenizer
+    from vila_b200.model import loading
+    assert (IGNORE_INDEX, DEFAULT_IMAGE_TOKEN, SENTINEL_TOKEN) == (-100, "<image>", "<vila/sentinel>")
+    assert MEDIA_TOKENS == {"image": "<image>", "video": "<vila/video>"} and make_list("a") == ["a"]
+    cfg = SimpleNamespace(num_video_frames=8, fps=0.0)
+    for c in json.loads((GOLDEN / "extract_media.json").read_text()):
+        parts = build_prompt_parts([tuple(x) for x in c["spec"]], tmp_path, llava.Image, llava.Video)
+        conv = [{"from": "human", "value": parts if len(parts) > 1 or not isinstance(parts[0], str) else parts[0]}]
+        media = extract_media(conv, cfg)
+        assert conv[0]["value"] == c["text"] and [list(im.size) for im in media["image"]] == c["image_sizes"], c["label"]
+    want = json.loads((GOLDEN / "tokenizer_setup.json").read_text())
+    tok = loading.prepare_tokenizer(toy_chat_tokenizer())
+    assert sorted(infer_stop_tokens(tok)) == want["stop_tokens"]
+    for case in want["conversations"]:
+        ids = tokenize_conversation(copy.deepcopy(case["conversation"]), tok, **case["kwargs"])
+        assert ids.tolist() == case["input_ids"], case["kwargs"]
+    with pytest.raises(ValueError):
+        tokenize_conversation([{"from": "robot", "value": "x"}], tok)
