@@ -355,3 +355,20 @@ def test_llava_utils_shim_matches_reference_fixture(tmp_path):
         assert ids.tolist() == case["input_ids"], case["kwargs"]
     with pytest.raises(ValueError):
         tokenize_conversation([{"from": "robot", "value": "x"}], tok)
+
+
+def test_unsupported_generation_options_are_refused_not_swallowed():
+    """HF `generate` options this decode loop does not implement (beams, repetition penalty, stopping
+    criteria ...) must raise, while every neutral setting — including a stock GenerationConfig, which the
+    reference's default_generation_config copies — passes."""
+    from transformers import GenerationConfig
+    from vila_b200.model.qwen2 import Qwen2ForCausalLM, unsupported_generation_options as refused
+    assert refused(None, {}) == [] and refused(GenerationConfig(), {}) == []
+    assert refused(SimpleNamespace(max_new_tokens=8, do_sample=True, temperature=0.2, top_p=0.9), {"num_beams": 1}) == []
+    assert refused(GenerationConfig(num_beams=4, repetition_penalty=1.2), {}) == ["num_beams=4", "repetition_penalty=1.2"]
+    assert refused(GenerationConfig(num_beams=4), {"num_beams": 1}) == []          # explicit kwargs win, as in HF
+    assert refused(None, {"stopping_criteria": []}) == [] and refused(None, {"stopping_criteria": [object]}) != []
+    llm = object.__new__(Qwen2ForCausalLM)
+    llm.generation_config = None
+    with pytest.raises(NotImplementedError, match="num_return_sequences=3"):
+        Qwen2ForCausalLM.generate.__wrapped__(llm, torch.zeros(1, 4, 8), num_return_sequences=3)

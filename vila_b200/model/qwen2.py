@@ -104,6 +104,30 @@ class PagedKVCache:
         return self.pool[layer, 1]
 
 
+# HF generate options that would change the output and that this decode loop does not implement: they
+# are refused instead of being swallowed by **kw (value = the settings that mean "off").
+_NEUTRAL_GENERATION_OPTIONS = {
+    "num_beams": (None, 1), "num_beam_groups": (None, 1), "num_return_sequences": (None, 1),
+    "repetition_penalty": (None, 1.0), "no_repeat_ngram_size": (None, 0), "min_new_tokens": (None, 0),
+    "min_length": (None, 0), "penalty_alpha": (None, 0.0), "typical_p": (None, 1.0), "min_p": (None,),
+    "bad_words_ids": (None,), "force_words_ids": (None,), "prefix_allowed_tokens_fn": (None,),
+    "assistant_model": (None,), "streamer": (None,), "stopping_criteria": (None,),
+}
+
+
+def unsupported_generation_options(generation_config, kwargs) -> List[str]:
+    """Names (with values) of result-changing HF generation options set to something other than off,
+    looked up in the explicit kwargs first and in the generation config otherwise."""
+    bad = []
+    for name, neutral in _NEUTRAL_GENERATION_OPTIONS.items():
+        v = kwargs[name] if name in kwargs else (getattr(generation_config, name, None) if generation_config is not None else None)
+        if name == "stopping_criteria" and v is not None and len(v) == 0:
+            continue
+        if not any(v is n or (n is not None and v == n) for n in neutral):
+            bad.append(f"{name}={v!r}")
+    return bad
+
+
 class Qwen2ForCausalLM(nn.Module):
     def __init__(self, cfg: Qwen2Config, device="cuda", dtype=torch.bfloat16):
         super().__init__()
@@ -333,6 +357,10 @@ class Qwen2ForCausalLM(nn.Module):
         [B, <=max_new_tokens] (pad-filled after EOS).  sp_runner: a sp.SequenceParallelPrefill ->
         the prompt is prefilled sequence-parallel across its group (greedy, batch size 1)."""
         gc = generation_config or self.generation_config
+        refused = unsupported_generation_options(gc, kw)
+        if refused:
+            raise NotImplementedError("generate: greedy / temperature-top-k-top-p sampling / logits processors are "
+                                      "implemented; not " + ", ".join(refused))
 
         def pick(name, given, default):
             if given is not None:
