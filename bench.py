@@ -20,7 +20,7 @@ mm_projector -> text/media splice -> Qwen2-7B prefill (S = 257 visual + 22 text 
   batched_decode  serving follow-up: 8 concurrent copies of the request, continuous batching over one
                   shared paged pool (vila_b200/serving.py): aggregate tok/s
   tiled_image     BASELINE configs[3]: a dynamic-S2 tiled image (35 tiles of 448^2 -> tower -> S2 merge ->
-                  projector) through encode_images, with its tensor-core floor (rank 0, last block of the run)
+                  projector) through encode_images, with its tensor-core floor (N = 1 runs only; last block of the run)
   sp_prefill      BASELINE configs[4]: LongVILA 256 frames (S = 65,814), sequence-parallel over ALL
                   ranks of this launch through LlavaLlamaModel.generate(max_new_tokens=1) with
                   vila_b200.sp enabled; first-token id + last-token logits top-5 / checksum so runs at
@@ -622,7 +622,7 @@ def run_ours(args):
         cpu = cpu_reference(cfg, seconds_budget=args.cpu_budget)["cpu_baseline"]
     dec_obj = llm.decoder(NEW_TOKENS)
     tiled = None
-    if not (args.profile or args.no_video):
+    if world == 1 and not (args.profile or args.no_video):
         try:  # last GPU work of the run; the headline line must survive a failure of this extra block
             tiled = tiled_image_block(peaks)
         except Exception as e:
